@@ -1,0 +1,42 @@
+"""In-tree build of libovn_b200.so (nvcc, sm_100a only).  The built .so is git-ignored but ships
+with the repo snapshot to the GPU box; nothing is JIT-compiled at import time."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libovn_b200.so')
+PROBE = os.path.join(HERE, 'umma_probe')
+SOURCES = ['api.cu', 'projection.cu', 'network_fp32.cu', 'network_tc.cu']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '-Xcompiler', '-fPIC']
+
+
+def _newer(target, deps):
+  if not os.path.exists(target):
+    return True
+  t = os.path.getmtime(target)
+  return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+  """Compile every CUDA source for sm_100a into overlapnet_b200/libovn_b200.so."""
+  nvcc = os.environ.get('NVCC', 'nvcc')
+  srcs = [os.path.join(CSRC, s) for s in SOURCES]
+  deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
+  deps.append(os.path.join(HERE, '..', 'include', 'ovn_b200.h'))
+  if force or _newer(LIB, deps):
+    cmd = [nvcc] + NVCC_FLAGS + ['-shared', '-o', LIB] + srcs
+    if verbose:
+      cmd.insert(1, '-Xptxas=-v')
+      print(' '.join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+  probe_src = os.path.join(CSRC, 'umma_probe.cu')
+  if os.path.exists(probe_src) and (force or _newer(PROBE, [probe_src] + deps)):
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ['-o', PROBE, probe_src])
+  return LIB
+
+
+if __name__ == '__main__':
+  print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

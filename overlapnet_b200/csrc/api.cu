@@ -1,0 +1,496 @@
+// api.cu -- the C ABI declared in include/ovn_b200.h: handle lifetime, weights, stage dispatch
+// and the host-buffer convenience entry points.  No CPU fallback exists anywhere in this library:
+// without an sm_100 device ovn_create fails with OVN_ERR_NO_DEVICE.
+#include "common.cuh"
+#include <math.h>
+#include <string.h>
+
+using namespace ovn;
+
+static const char* kLegNames[] = {"s_conv1", "s_conv2", "s_conv3", "s_conv3a", "s_conv4", "s_conv5",
+                                  "s_conv6", "s_conv7", "s_conv8", "s_conv9", "s_conv10"};
+
+static void set_spec(ConvSpec& L, const char* name, int kh, int kw, int sh, int sw, int cin, int cout, int relu,
+                     int h_in, int w_in) {
+  memset(&L, 0, sizeof(L));
+  snprintf(L.name, sizeof(L.name), "%s", name);
+  L.kh = kh; L.kw = kw; L.sh = sh; L.sw = sw; L.cin = cin; L.cout = cout; L.relu = relu;
+  L.h_in = h_in; L.w_in = w_in;
+  L.h_out = (h_in - kh) / sh + 1;
+  L.w_out = (w_in - kw) / sw + 1;
+}
+
+static __global__ void k_iota(int32_t* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+extern "C" {
+
+int ovn_abi_version(void) { return OVN_ABI_VERSION; }
+
+const char* ovn_status_string(int status) {
+  switch (status) {
+    case OVN_OK: return "OVN_OK";
+    case OVN_ERR_INVALID_ARG: return "OVN_ERR_INVALID_ARG";
+    case OVN_ERR_BAD_CONFIG: return "OVN_ERR_BAD_CONFIG";
+    case OVN_ERR_WEIGHTS: return "OVN_ERR_WEIGHTS";
+    case OVN_ERR_CUDA: return "OVN_ERR_CUDA";
+    case OVN_ERR_NO_DEVICE: return "OVN_ERR_NO_DEVICE";
+    case OVN_ERR_CAPACITY: return "OVN_ERR_CAPACITY";
+    default: return "OVN_ERR_UNKNOWN";
+  }
+}
+
+void ovn_default_config(ovn_config* c) {
+  if (!c) return;
+  memset(c, 0, sizeof(*c));
+  c->abi_version = OVN_ABI_VERSION;
+  c->proj_H = 64; c->proj_W = 900;                 // config/network.yml:75
+  c->fov_up_deg = 3.0f; c->fov_down_deg = -25.0f;  // utils.py:59
+  c->max_range = 50.0f;
+  c->use_depth = 1; c->use_normals = 1;            // network.yml:20-24
+  c->n_prob_channels = 0; c->use_intensity = 0;
+  c->strides_layer1[0] = 2; c->strides_layer1[1] = 2;   // network.yml:79
+  c->additional_unsymmetric_layer3a = 1;           // network.yml:82
+  c->leg_output_width = 360;                       // network.yml:77
+  c->conv1size = 15;                               // generateNet.py:88-89
+  c->precision = OVN_PREC_F16_TC;
+  c->max_batch_scans = 16;                         // network.yml:41 batch_size
+  c->max_batch_pairs = 1101;
+}
+
+static thread_local std::string g_create_error;
+
+const char* ovn_last_error(const ovn_handle* h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
+int64_t ovn_launch_count(const ovn_handle* h) { return h ? h->launches : 0; }
+int ovn_input_channels(const ovn_handle* h) { return h ? h->C : 0; }
+int ovn_feature_width(const ovn_handle* h) { return h ? h->cfg.leg_output_width : 0; }
+int ovn_feature_channels(const ovn_handle* h) { return h ? kFeatC : 0; }
+
+#define CREATE_FAIL(code, ...)                              \
+  do {                                                      \
+    char _b[512];                                           \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);                  \
+    g_create_error = _b;                                    \
+    if (h) ovn_destroy(h);                                  \
+    return (code);                                          \
+  } while (0)
+
+#define CREATE_CUDA(call)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (call);                                                           \
+    if (_e != cudaSuccess) CREATE_FAIL(OVN_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+int ovn_create(const ovn_config* cfg, ovn_handle** out) {
+  ovn_handle* h = nullptr;
+  if (!cfg || !out) CREATE_FAIL(OVN_ERR_INVALID_ARG, "ovn_create: NULL argument");
+  *out = nullptr;
+  if (cfg->abi_version != OVN_ABI_VERSION)
+    CREATE_FAIL(OVN_ERR_INVALID_ARG, "ovn_create: abi_version %d != %d", cfg->abi_version, OVN_ABI_VERSION);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    CREATE_FAIL(OVN_ERR_NO_DEVICE, "ovn_create: no CUDA device visible (this library has no CPU fallback)");
+  }
+  int dev = 0;
+  CREATE_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CREATE_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    CREATE_FAIL(OVN_ERR_NO_DEVICE, "ovn_create: device %d is sm_%d%d; this build targets sm_100a only", dev,
+                prop.major, prop.minor);
+  h = new ovn_handle();
+  h->cfg = *cfg;
+  h->device = dev;
+  h->sm_count = prop.multiProcessorCount;
+  const ovn_config& c = h->cfg;
+  if (c.proj_H <= 0 || c.proj_W <= 0 || c.max_batch_scans <= 0 || c.max_batch_pairs <= 0)
+    CREATE_FAIL(OVN_ERR_BAD_CONFIG, "ovn_create: non-positive size in config");
+  if (c.n_prob_channels != 0 && c.n_prob_channels != 3 && c.n_prob_channels != 20)
+    CREATE_FAIL(OVN_ERR_BAD_CONFIG, "ovn_create: n_prob_channels must be 0, 3 or 20 (infer.py:68-73)");
+  h->C = (c.use_depth ? 1 : 0) + (c.use_normals ? 3 : 0) + c.n_prob_channels + (c.use_intensity ? 1 : 0);
+  if (h->C <= 0) CREATE_FAIL(OVN_ERR_BAD_CONFIG, "ovn_create: no input channel enabled");
+
+  // ---- leg shape inference (generateNet.py:161-217).  A config whose leg does not reduce the image
+  // to 1 x leg_output_width x 128 still gets a handle, but only the projection stages work on it.
+  struct { int kh, kw, sh, sw, cout; bool opt; } T[] = {
+      {5, 15, c.strides_layer1[0], c.strides_layer1[1], 16, false}, {3, 15, 2, 1, 32, false},
+      {3, 15, 2, 1, 64, false},  {3, 12, 2, 1, 64, true},           {2, 9, 2, 1, 128, false},
+      {1, 9, 1, 1, 128, false},  {1, 9, 1, 1, 128, false},          {1, 9, 1, 1, 128, false},
+      {1, 7, 1, 1, 128, false},  {1, 5, 1, 1, 128, false},          {1, 3, 1, 1, 128, false}};
+  int hh = c.proj_H, ww = c.proj_W, cc = h->C;
+  h->n_leg = 0;
+  h->net_ok = true;
+  char nb[256];
+  for (int i = 0; i < 11 && h->net_ok; ++i) {
+    if (T[i].opt && !c.additional_unsymmetric_layer3a) continue;
+    if (T[i].sh <= 0 || T[i].sw <= 0 || hh < T[i].kh || ww < T[i].kw) {
+      snprintf(nb, sizeof(nb), "layer %s does not fit its input %dx%d", kLegNames[i], hh, ww);
+      h->net_ok = false; h->net_error = nb;
+      break;
+    }
+    set_spec(h->leg[h->n_leg], kLegNames[i], T[i].kh, T[i].kw, T[i].sh, T[i].sw, cc, T[i].cout, 1, hh, ww);
+    hh = h->leg[h->n_leg].h_out; ww = h->leg[h->n_leg].w_out; cc = T[i].cout;
+    h->n_leg++;
+  }
+  const int Wf = c.leg_output_width, s = c.conv1size;
+  if (h->net_ok && (hh != 1 || ww != c.leg_output_width || cc != kFeatC)) {
+    snprintf(nb, sizeof(nb), "leg output is %dx%dx%d, expected 1x%dx%d (network.yml:77)", hh, ww, cc,
+             c.leg_output_width, kFeatC);
+    h->net_ok = false; h->net_error = nb;
+  }
+  if (h->net_ok && (s <= 0 || Wf % s != 0 || Wf / s < 3)) {
+    snprintf(nb, sizeof(nb), "conv1size %d must divide leg_output_width %d", s, Wf);
+    h->net_ok = false; h->net_error = nb;
+  }
+  if (!h->net_ok) { h->n_leg = 0; *out = nullptr; }
+  // ---- head shapes (generateNet.py:96-114)
+  if (h->net_ok) {
+    set_spec(h->head[0], "c_conv1", 1, s, 1, s, kFeatC, 64, 0, Wf, Wf);
+    set_spec(h->head[1], "c_conv2", s, 1, s, 1, 64, 128, 1, h->head[0].h_out, h->head[0].w_out);
+    set_spec(h->head[2], "c_conv3", 3, 3, 1, 1, 128, 256, 1, h->head[1].h_out, h->head[1].w_out);
+    h->o1_h = h->head[0].h_out; h->o1_w = h->head[0].w_out;
+    h->o2_h = h->head[1].h_out; h->o2_w = h->head[1].w_out;
+    h->o3_h = h->head[2].h_out; h->o3_w = h->head[2].w_out;
+    h->dense_in = h->o3_h * h->o3_w * h->head[2].cout;
+  }
+
+  // ---- workspaces
+  const size_t HW = (size_t)c.proj_H * c.proj_W;
+  CREATE_CUDA(cudaMalloc(&h->d_keys, (size_t)c.max_batch_scans * HW * sizeof(unsigned long long)));
+  CREATE_CUDA(cudaMalloc(&h->d_input, (size_t)c.max_batch_scans * HW * h->C * sizeof(float)));
+  size_t max_act = 1;
+  for (int l = 0; l < h->n_leg; ++l) {
+    size_t a = (size_t)h->leg[l].h_out * h->leg[l].w_out * h->leg[l].cout;
+    if (a > max_act) max_act = a;
+  }
+  h->cap_act = (int64_t)max_act * c.max_batch_scans;
+  CREATE_CUDA(cudaMalloc(&h->d_act[0], h->cap_act * sizeof(float)));
+  CREATE_CUDA(cudaMalloc(&h->d_act[1], h->cap_act * sizeof(float)));
+  CREATE_CUDA(cudaMalloc(&h->d_query_fv, (size_t)Wf * kFeatC * sizeof(float)));
+  CREATE_CUDA(cudaMalloc(&h->d_idx_tmp, (size_t)2 * c.max_batch_pairs * sizeof(int32_t)));
+  CREATE_CUDA(cudaMalloc(&h->d_logit, (size_t)c.max_batch_pairs * sizeof(float)));
+  if (c.precision == OVN_PREC_FP32 && h->net_ok) {
+    CREATE_CUDA(cudaMalloc(&h->d_o1, (size_t)c.max_batch_pairs * h->o1_h * h->o1_w * 64 * sizeof(float)));
+    CREATE_CUDA(cudaMalloc(&h->d_o2, (size_t)c.max_batch_pairs * h->o2_h * h->o2_w * 128 * sizeof(float)));
+    CREATE_CUDA(cudaMalloc(&h->d_G, (size_t)c.max_batch_pairs * Wf * Wf * sizeof(float)));
+  } else if (c.precision != OVN_PREC_F16_TC && c.precision != OVN_PREC_FP32) {
+    CREATE_FAIL(OVN_ERR_BAD_CONFIG, "ovn_create: unknown precision %d", c.precision);
+  }
+  CREATE_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  *out = h;
+  return OVN_OK;
+}
+
+int ovn_destroy(ovn_handle* h) {
+  if (!h) return OVN_OK;
+  tc_free(h);
+  for (auto& p : h->d_w) if (p) cudaFree(p);
+  for (auto& p : h->d_b) if (p) cudaFree(p);
+  for (auto& p : h->d_w16) if (p) cudaFree(p);
+  void* bufs[] = {h->d_keys, h->d_valid_words, h->d_word_prefix, h->d_scan_tmp, h->d_act[0], h->d_act[1],
+                  h->d_input, h->d_o1, h->d_o2, h->d_logit, h->d_G, h->d_idx_tmp, h->d_query_fv,
+                  h->d_stage_points, h->d_stage_offsets};
+  for (void* b : bufs) if (b) cudaFree(b);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return OVN_OK;
+}
+
+// ---- weights ------------------------------------------------------------------------------------
+static const ConvSpec* find_layer(const ovn_handle* h, const char* name, int* slot) {
+  for (int l = 0; l < h->n_leg; ++l)
+    if (strcmp(h->leg[l].name, name) == 0) { *slot = l; return &h->leg[l]; }
+  for (int l = 0; l < 3; ++l)
+    if (strcmp(h->head[l].name, name) == 0) { *slot = kMaxLegLayers + l; return &h->head[l]; }
+  return nullptr;
+}
+
+int ovn_set_weights(ovn_handle* h, const char* name, const float* k, const int64_t* dims, int32_t ndim,
+                    const float* bias, int64_t bias_len) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  if (!name || !k || !dims || !bias) OVN_SET_ERR(h, OVN_ERR_INVALID_ARG, "ovn_set_weights: NULL argument");
+  if (!h->net_ok) OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "ovn_set_weights: %s", h->net_error.c_str());
+  int slot = -1;
+  int64_t expect[4];
+  int expect_nd = 0;
+  int64_t expect_bias = 0;
+  if (strcmp(name, "overlap_output") == 0) {
+    expect[0] = h->dense_in; expect[1] = 1; expect_nd = 2; expect_bias = 1;
+  } else {
+    const ConvSpec* L = find_layer(h, name, &slot);
+    if (!L) OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "ovn_set_weights: unknown layer name '%s'", name);
+    expect[0] = L->kh; expect[1] = L->kw; expect[2] = L->cin; expect[3] = L->cout; expect_nd = 4;
+    expect_bias = L->cout;
+  }
+  if (ndim != expect_nd || bias_len != expect_bias)
+    OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "ovn_set_weights: layer %s expects a %d-d kernel and %lld biases", name,
+                expect_nd, (long long)expect_bias);
+  int64_t total = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (dims[i] != expect[i])
+      OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "ovn_set_weights: layer %s kernel dim %d is %lld, expected %lld", name, i,
+                  (long long)dims[i], (long long)expect[i]);
+    total *= dims[i];
+  }
+  LayerWeights& w = h->host_w[name];
+  w.kernel.assign(k, k + total);
+  w.dims.assign(dims, dims + ndim);
+  w.bias.assign(bias, bias + bias_len);
+  w.set = true;
+  h->weights_ready = false;
+  return OVN_OK;
+}
+
+static int upload(ovn_handle* h, int slot, const LayerWeights& w) {
+  if (h->d_w[slot]) { cudaFree(h->d_w[slot]); h->d_w[slot] = nullptr; }
+  if (h->d_b[slot]) { cudaFree(h->d_b[slot]); h->d_b[slot] = nullptr; }
+  OVN_CUDA(h, cudaMalloc(&h->d_w[slot], w.kernel.size() * sizeof(float)));
+  OVN_CUDA(h, cudaMalloc(&h->d_b[slot], w.bias.size() * sizeof(float)));
+  OVN_CUDA(h, cudaMemcpy(h->d_w[slot], w.kernel.data(), w.kernel.size() * sizeof(float), cudaMemcpyHostToDevice));
+  OVN_CUDA(h, cudaMemcpy(h->d_b[slot], w.bias.data(), w.bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return OVN_OK;
+}
+
+int ovn_finalize_weights(ovn_handle* h) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  if (!h->net_ok) OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "ovn_finalize_weights: %s", h->net_error.c_str());
+  for (int l = 0; l < h->n_leg; ++l) {
+    auto it = h->host_w.find(h->leg[l].name);
+    if (it == h->host_w.end() || !it->second.set)
+      OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "ovn_finalize_weights: layer %s has no weights", h->leg[l].name);
+    int rc = upload(h, l, it->second);
+    if (rc != OVN_OK) return rc;
+  }
+  const char* hn[4] = {"c_conv1", "c_conv2", "c_conv3", "overlap_output"};
+  for (int l = 0; l < 4; ++l) {
+    auto it = h->host_w.find(hn[l]);
+    if (it == h->host_w.end() || !it->second.set)
+      OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "ovn_finalize_weights: layer %s has no weights", hn[l]);
+    int rc = upload(h, kMaxLegLayers + l, it->second);
+    if (rc != OVN_OK) return rc;
+  }
+  if (h->cfg.precision == OVN_PREC_F16_TC) {
+    int rc = tc_pack_weights(h);
+    if (rc != OVN_OK) return rc;
+  }
+  h->weights_ready = true;
+  return OVN_OK;
+}
+
+// ---- stage entry points ---------------------------------------------------------------------------
+#define REQUIRE(h, cond, msg) \
+  do { if (!(cond)) OVN_SET_ERR(h, OVN_ERR_INVALID_ARG, "%s: %s", __func__, msg); } while (0)
+
+int ovn_project_batch(ovn_handle* h, const float* d_points, const int64_t* d_offsets, int32_t n_scans,
+                      int64_t n_total, float max_range, float* d_range, float* d_vertex, float* d_intensity,
+                      int32_t* d_idx, void* stream) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  REQUIRE(h, n_scans >= 0 && n_total >= 0, "negative size");
+  REQUIRE(h, n_scans == 0 || d_offsets, "d_offsets is NULL");
+  REQUIRE(h, n_total == 0 || d_points, "d_points is NULL");
+  return project_batch(h, d_points, d_offsets, n_scans, n_total, max_range, d_range, d_vertex, d_intensity, d_idx,
+                       (cudaStream_t)stream);
+}
+
+int ovn_normals_batch(ovn_handle* h, const float* d_range, const float* d_vertex, int32_t n_scans, float* d_normal,
+                      void* stream) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  REQUIRE(h, n_scans >= 0, "negative size");
+  REQUIRE(h, n_scans == 0 || (d_range && d_vertex && d_normal), "NULL image pointer");
+  return normals_batch(h, d_range, d_vertex, n_scans, d_normal, (cudaStream_t)stream);
+}
+
+int ovn_semantic_batch(ovn_handle* h, const int32_t* d_idx, const float* d_probs, const int64_t* d_offsets,
+                       int32_t n_scans, int32_t n_classes, float* d_out, void* stream) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  REQUIRE(h, n_scans >= 0 && n_classes > 0, "bad size");
+  REQUIRE(h, n_scans == 0 || (d_idx && d_probs && d_offsets && d_out), "NULL pointer");
+  return semantic_batch(h, d_idx, d_probs, d_offsets, n_scans, n_classes, d_out, (cudaStream_t)stream);
+}
+
+int ovn_preprocess_batch(ovn_handle* h, const float* d_points, const int64_t* d_offsets, int32_t n_scans,
+                         int64_t n_total, const float* d_probs, float* d_input, void* stream) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  REQUIRE(h, n_scans >= 0 && n_total >= 0, "negative size");
+  REQUIRE(h, n_scans == 0 || (d_offsets && d_input), "NULL pointer");
+  return preprocess_batch(h, d_points, d_offsets, n_scans, n_total, d_probs, d_input, (cudaStream_t)stream);
+}
+
+int ovn_pack_input(ovn_handle* h, const float* d_depth, const float* d_normal, const float* d_prob,
+                   const float* d_intensity, int32_t n_scans, float* d_input, void* stream) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  REQUIRE(h, n_scans >= 0, "negative size");
+  REQUIRE(h, (d_depth != nullptr) == (h->cfg.use_depth != 0), "depth pointer does not match use_depth");
+  REQUIRE(h, (d_normal != nullptr) == (h->cfg.use_normals != 0), "normal pointer does not match use_normals");
+  REQUIRE(h, (d_prob != nullptr) == (h->cfg.n_prob_channels != 0), "prob pointer does not match n_prob_channels");
+  REQUIRE(h, (d_intensity != nullptr) == (h->cfg.use_intensity != 0), "intensity pointer does not match use_intensity");
+  return pack_input(h, d_depth, d_normal, d_prob, d_intensity, n_scans, d_input, (cudaStream_t)stream);
+}
+
+int ovn_leg_forward(ovn_handle* h, const float* d_input, int32_t n_scans, float* d_fv, void* stream) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  REQUIRE(h, n_scans >= 0, "negative size");
+  if (n_scans == 0) return OVN_OK;
+  REQUIRE(h, d_input && d_fv, "NULL pointer");
+  if (!h->net_ok) OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "ovn_leg_forward: %s", h->net_error.c_str());
+  if (!h->weights_ready) OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "ovn_leg_forward: weights not finalised");
+  const int Wf = h->cfg.leg_output_width;
+  const size_t in_stride = (size_t)h->cfg.proj_H * h->cfg.proj_W * h->C;
+  for (int s0 = 0; s0 < n_scans; s0 += h->cfg.max_batch_scans) {
+    const int n = (n_scans - s0 < h->cfg.max_batch_scans) ? n_scans - s0 : h->cfg.max_batch_scans;
+    int rc = (h->cfg.precision == OVN_PREC_F16_TC)
+                 ? leg_forward_tc(h, d_input + s0 * in_stride, n, d_fv + (size_t)s0 * Wf * kFeatC, (cudaStream_t)stream)
+                 : leg_forward_fp32(h, d_input + s0 * in_stride, n, d_fv + (size_t)s0 * Wf * kFeatC, (cudaStream_t)stream);
+    if (rc != OVN_OK) return rc;
+  }
+  return OVN_OK;
+}
+
+static int heads_dispatch(ovn_handle* h, const float* d_bank, const float* d_query, const int32_t* d_left,
+                          const int32_t* d_right, int n, float* d_overlap, int32_t* d_yaw, float* d_corr,
+                          cudaStream_t s) {
+  if (!h->net_ok) OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "heads: %s", h->net_error.c_str());
+  if (!h->weights_ready) OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "heads: weights not finalised");
+  return (h->cfg.precision == OVN_PREC_F16_TC)
+             ? heads_forward_tc(h, d_bank, d_query, d_left, d_right, n, d_overlap, d_yaw, d_corr, s)
+             : heads_forward_fp32(h, d_bank, d_query, d_left, d_right, n, d_overlap, d_yaw, d_corr, s);
+}
+
+int ovn_heads_forward(ovn_handle* h, const float* d_bank, int64_t bank_size, const int32_t* d_left,
+                      const int32_t* d_right, int32_t n_pairs, float* d_overlap, int32_t* d_yaw, float* d_corr,
+                      void* stream) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  REQUIRE(h, n_pairs >= 0 && bank_size >= 0, "negative size");
+  if (n_pairs == 0) return OVN_OK;
+  REQUIRE(h, d_bank && d_left && d_right && d_overlap && d_yaw, "NULL pointer");
+  return heads_dispatch(h, d_bank, nullptr, d_left, d_right, n_pairs, d_overlap, d_yaw, d_corr, (cudaStream_t)stream);
+}
+
+int ovn_heads_1vsN(ovn_handle* h, const float* d_bank, int64_t bank_size, const float* d_query,
+                   const int32_t* d_cand_idx, int32_t n_cand, float* d_overlap, int32_t* d_yaw, float* d_corr,
+                   void* stream) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  REQUIRE(h, n_cand >= 0 && bank_size >= 0, "negative size");
+  if (n_cand == 0) return OVN_OK;
+  REQUIRE(h, d_bank && d_query && d_overlap && d_yaw, "NULL pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (d_cand_idx) return heads_dispatch(h, d_bank, d_query, d_cand_idx, nullptr, n_cand, d_overlap, d_yaw, d_corr, s);
+  // candidates 0..n-1 in chunks of the scratch capacity
+  const int maxp = h->cfg.max_batch_pairs;
+  for (int p0 = 0; p0 < n_cand; p0 += maxp) {
+    const int np = (n_cand - p0 < maxp) ? n_cand - p0 : maxp;
+    k_iota<<<(np + 255) / 256, 256, 0, s>>>(h->d_idx_tmp, np);
+    OVN_LAUNCH_CHECK(h);
+    int rc = heads_dispatch(h, d_bank + (size_t)p0 * h->cfg.leg_output_width * kFeatC, d_query, h->d_idx_tmp, nullptr,
+                            np, d_overlap + p0, d_yaw + p0,
+                            d_corr ? d_corr + (size_t)p0 * h->cfg.leg_output_width : nullptr, s);
+    if (rc != OVN_OK) return rc;
+  }
+  return OVN_OK;
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------------
+static int ensure_stage(ovn_handle* h, int64_t n_points, int n_scans) {
+  if (n_points > h->cap_stage_points) {
+    if (h->d_stage_points) cudaFree(h->d_stage_points);
+    h->d_stage_points = nullptr;
+    const int64_t cap = n_points + n_points / 8 + 4096;
+    OVN_CUDA(h, cudaMalloc(&h->d_stage_points, cap * 4 * sizeof(float)));
+    h->cap_stage_points = cap;
+  }
+  if (!h->d_stage_offsets) OVN_CUDA(h, cudaMalloc(&h->d_stage_offsets, ((size_t)h->cfg.max_batch_scans + 1) * sizeof(int64_t)));
+  (void)n_scans;
+  return OVN_OK;
+}
+
+int ovn_encode_clouds_host(ovn_handle* h, const float* h_points, const int64_t* h_offsets, int32_t n_scans,
+                           float* h_fv) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  REQUIRE(h, n_scans >= 0, "negative size");
+  if (n_scans == 0) return OVN_OK;
+  REQUIRE(h, h_points && h_offsets && h_fv, "NULL pointer");
+  if (h->cfg.n_prob_channels != 0)
+    OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "ovn_encode_clouds_host: semantic channels need per-point probabilities; "
+                "use the device-pointer stages");
+  cudaStream_t s = h->own_stream;
+  const int Wf = h->cfg.leg_output_width;
+  float* d_fv = nullptr;
+  OVN_CUDA(h, cudaMalloc(&d_fv, (size_t)h->cfg.max_batch_scans * Wf * kFeatC * sizeof(float)));
+  int rc = OVN_OK;
+  for (int s0 = 0; s0 < n_scans && rc == OVN_OK; s0 += h->cfg.max_batch_scans) {
+    const int n = (n_scans - s0 < h->cfg.max_batch_scans) ? n_scans - s0 : h->cfg.max_batch_scans;
+    const int64_t p0 = h_offsets[s0], p1 = h_offsets[s0 + n];
+    rc = ensure_stage(h, p1 - p0, n);
+    if (rc != OVN_OK) break;
+    std::vector<int64_t> rel(n + 1);
+    for (int i = 0; i <= n; ++i) rel[i] = h_offsets[s0 + i] - p0;
+    cudaError_t e = cudaMemcpyAsync(h->d_stage_points, h_points + p0 * 4, (p1 - p0) * 4 * sizeof(float),
+                                    cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_stage_offsets, rel.data(), (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // rel is a stack-lifetime buffer
+    if (e != cudaSuccess) { h->last_error = cudaGetErrorString(e); rc = OVN_ERR_CUDA; break; }
+    rc = preprocess_batch(h, h->d_stage_points, h->d_stage_offsets, n, p1 - p0, nullptr, h->d_input, s);
+    if (rc == OVN_OK) rc = ovn_leg_forward(h, h->d_input, n, d_fv, s);
+    if (rc == OVN_OK) {
+      e = cudaMemcpyAsync(h_fv + (size_t)s0 * Wf * kFeatC, d_fv, (size_t)n * Wf * kFeatC * sizeof(float),
+                          cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) { h->last_error = cudaGetErrorString(e); rc = OVN_ERR_CUDA; }
+    }
+  }
+  cudaFree(d_fv);
+  return rc;
+}
+
+int ovn_query_cloud_vs_bank_host(ovn_handle* h, const float* h_points, int64_t n_points, const float* d_bank,
+                                 int64_t bank_size, const int32_t* h_cand_idx, int32_t n_cand, float* h_overlap,
+                                 int32_t* h_yaw, float* h_query_fv) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  REQUIRE(h, n_points >= 0 && n_cand >= 0, "negative size");
+  REQUIRE(h, h_points, "h_points is NULL");
+  REQUIRE(h, n_cand == 0 || (d_bank && h_overlap && h_yaw), "NULL pointer");
+  REQUIRE(h, n_cand <= h->cfg.max_batch_pairs || h_cand_idx == nullptr, "n_cand exceeds max_batch_pairs");
+  if (h->cfg.n_prob_channels != 0)
+    OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "ovn_query_cloud_vs_bank_host: semantic channels are not supported here");
+  cudaStream_t s = h->own_stream;
+  int rc = ensure_stage(h, n_points, 1);
+  if (rc != OVN_OK) return rc;
+  const int Wf = h->cfg.leg_output_width;
+  // results staging on device: overlap in d_logit, yaw in d_idx_tmp[max_pairs..]
+  if (n_cand > h->cfg.max_batch_pairs)
+    OVN_SET_ERR(h, OVN_ERR_CAPACITY, "n_cand=%d exceeds max_batch_pairs=%d", n_cand, h->cfg.max_batch_pairs);
+  const int64_t offs[2] = {0, n_points};
+  OVN_CUDA(h, cudaMemcpyAsync(h->d_stage_points, h_points, (size_t)n_points * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
+  OVN_CUDA(h, cudaMemcpyAsync(h->d_stage_offsets, offs, sizeof(offs), cudaMemcpyHostToDevice, s));
+  if (h_cand_idx && n_cand > 0)
+    OVN_CUDA(h, cudaMemcpyAsync(h->d_idx_tmp, h_cand_idx, (size_t)n_cand * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  OVN_CUDA(h, cudaStreamSynchronize(s));   // offs / caller buffers may be pageable
+  rc = preprocess_batch(h, h->d_stage_points, h->d_stage_offsets, 1, n_points, nullptr, h->d_input, s);
+  if (rc != OVN_OK) return rc;
+  rc = ovn_leg_forward(h, h->d_input, 1, h->d_query_fv, s);
+  if (rc != OVN_OK) return rc;
+  if (n_cand > 0) {
+    int32_t* d_yaw = h->d_idx_tmp + h->cfg.max_batch_pairs;
+    if (h_cand_idx) {
+      rc = heads_dispatch(h, d_bank, h->d_query_fv, h->d_idx_tmp, nullptr, n_cand, h->d_logit, d_yaw, nullptr, s);
+    } else {
+      k_iota<<<(n_cand + 255) / 256, 256, 0, s>>>(h->d_idx_tmp, n_cand);
+      OVN_LAUNCH_CHECK(h);
+      rc = heads_dispatch(h, d_bank, h->d_query_fv, h->d_idx_tmp, nullptr, n_cand, h->d_logit, d_yaw, nullptr, s);
+    }
+    if (rc != OVN_OK) return rc;
+    OVN_CUDA(h, cudaMemcpyAsync(h_overlap, h->d_logit, (size_t)n_cand * sizeof(float), cudaMemcpyDeviceToHost, s));
+    OVN_CUDA(h, cudaMemcpyAsync(h_yaw, d_yaw, (size_t)n_cand * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  }
+  if (h_query_fv)
+    OVN_CUDA(h, cudaMemcpyAsync(h_query_fv, h->d_query_fv, (size_t)Wf * kFeatC * sizeof(float), cudaMemcpyDeviceToHost, s));
+  OVN_CUDA(h, cudaStreamSynchronize(s));
+  (void)bank_size;
+  return OVN_OK;
+}
+
+}  // extern "C"

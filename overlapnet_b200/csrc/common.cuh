@@ -1,0 +1,139 @@
+// common.cuh -- handle, error plumbing and small device helpers shared by all translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/ovn_b200.h"
+
+namespace ovn {
+
+constexpr int kFeatC = 128;           // leg output channels (generateNet.py:214)
+constexpr int kMaxLegLayers = 12;
+
+struct ConvSpec {                      // one Conv2D layer (valid padding, bias)
+  char name[24];
+  int kh, kw, sh, sw, cin, cout;
+  int relu;
+  int h_in, w_in, h_out, w_out;
+};
+
+struct LayerWeights {
+  std::vector<float> kernel;           // Keras layout, flattened
+  std::vector<int64_t> dims;
+  std::vector<float> bias;
+  bool set = false;
+};
+
+}  // namespace ovn
+
+struct ovn_handle {
+  ovn_config cfg;
+  int device = 0;
+  int sm_count = 0;
+  std::string last_error;
+  int64_t launches = 0;
+
+  int C = 0;                            // input channels (infer.py:61-73)
+  int n_leg = 0;
+  ovn::ConvSpec leg[ovn::kMaxLegLayers];
+  ovn::ConvSpec head[3];                // c_conv1..3 in "delta image" coordinates
+  int o1_h = 0, o1_w = 0;               // c_conv1 output (360, 24)
+  int o2_h = 0, o2_w = 0;               // c_conv2 output (24, 24)
+  int o3_h = 0, o3_w = 0;               // c_conv3 output (22, 22)
+  int dense_in = 0;
+
+  std::map<std::string, ovn::LayerWeights> host_w;
+  bool weights_ready = false;
+  bool net_ok = false;                 // leg/head shapes valid for this config (else projection only)
+  std::string net_error;
+
+  // device weights, fp32 GEMM layout [K][N] (K = kh*kw*cin, Keras HWIO flattened is already that)
+  float* d_w[ovn::kMaxLegLayers + 4] = {};
+  float* d_b[ovn::kMaxLegLayers + 4] = {};
+  // fp16 packed weights for the tensor-core path (layout documented in network_tc.cu)
+  __half* d_w16[ovn::kMaxLegLayers + 4] = {};
+
+  // workspaces
+  unsigned long long* d_keys = nullptr;      // [max_batch_scans][H*W] atomic-min keys
+  uint32_t* d_valid_words = nullptr;         // validity bitmask, 1 bit per point
+  uint32_t* d_word_prefix = nullptr;         // exclusive prefix of popcounts
+  uint32_t* d_scan_tmp = nullptr;
+  int64_t cap_points = 0;
+  float* d_act[2] = {nullptr, nullptr};      // ping-pong activations for the leg
+  int64_t cap_act = 0;
+  float* d_input = nullptr;                  // [max_batch_scans][H][W][C]
+  float* d_o1 = nullptr;                     // [max_batch_pairs][360][24][64]
+  float* d_o2 = nullptr;                     // [max_batch_pairs][24][24][128]
+  float* d_logit = nullptr;                  // [max_batch_pairs]
+  float* d_G = nullptr;                      // [max_batch_pairs][360][360] (fp32 path corr)
+  int32_t* d_idx_tmp = nullptr;              // [max_batch_pairs] x2 scratch for 1vsN index lists
+  float* d_query_fv = nullptr;               // [360][128]
+  float* d_stage_points = nullptr;           // host-entry staging of clouds
+  int64_t cap_stage_points = 0;
+  int64_t* d_stage_offsets = nullptr;
+  void* h_pinned = nullptr;                  // pinned staging for host entry points
+  int64_t cap_pinned = 0;
+  cudaStream_t own_stream = nullptr;
+};
+
+#define OVN_SET_ERR(h, code, ...)                                 \
+  do {                                                            \
+    char _buf[512];                                               \
+    snprintf(_buf, sizeof(_buf), __VA_ARGS__);                    \
+    (h)->last_error = _buf;                                       \
+    return (code);                                                \
+  } while (0)
+
+#define OVN_CUDA(h, call)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (call);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      OVN_SET_ERR(h, OVN_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,     \
+                  cudaGetErrorString(_e));                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define OVN_LAUNCH_CHECK(h)                                                                 \
+  do {                                                                                      \
+    (h)->launches++;                                                                        \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess) {                                                                \
+      OVN_SET_ERR(h, OVN_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__, \
+                  cudaGetErrorString(_e));                                                  \
+    }                                                                                       \
+  } while (0)
+
+namespace ovn {
+
+// ---- stage entry points implemented in the .cu files (called from api.cu) -------------------
+int project_batch(ovn_handle* h, const float* d_points, const int64_t* d_offsets, int n_scans,
+                  int64_t n_total, float max_range, float* d_range, float* d_vertex,
+                  float* d_intensity, int32_t* d_idx, cudaStream_t s);
+int normals_batch(ovn_handle* h, const float* d_range, const float* d_vertex, int n_scans,
+                  float* d_normal, cudaStream_t s);
+int semantic_batch(ovn_handle* h, const int32_t* d_idx, const float* d_probs,
+                   const int64_t* d_offsets, int n_scans, int n_classes, float* d_out,
+                   cudaStream_t s);
+int preprocess_batch(ovn_handle* h, const float* d_points, const int64_t* d_offsets, int n_scans,
+                     int64_t n_total, const float* d_probs, float* d_input, cudaStream_t s);
+int pack_input(ovn_handle* h, const float* d_depth, const float* d_normal, const float* d_prob,
+               const float* d_intensity, int n_scans, float* d_input, cudaStream_t s);
+
+int leg_forward_fp32(ovn_handle* h, const float* d_input, int n, float* d_fv, cudaStream_t s);
+int heads_forward_fp32(ovn_handle* h, const float* d_bank, const float* d_query,
+                       const int32_t* d_left, const int32_t* d_right, int n, float* d_overlap,
+                       int32_t* d_yaw, float* d_corr, cudaStream_t s);
+
+int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cudaStream_t s);
+int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query,
+                     const int32_t* d_left, const int32_t* d_right, int n, float* d_overlap,
+                     int32_t* d_yaw, float* d_corr, cudaStream_t s);
+int tc_pack_weights(ovn_handle* h);
+void tc_free(ovn_handle* h);
+
+}  // namespace ovn
