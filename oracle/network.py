@@ -157,18 +157,35 @@ def readout(overlap, corr):
   return np.asarray(overlap, np.float32), 180 - np.argmax(corr, axis=1)
 
 
-def heads_forward(l_fv, r_fv, weights, model_cfg=None, dtype=torch.float64, batch=4):
+def heads_forward(l_fv, r_fv, weights, model_cfg=None, dtype=torch.float64, batch=4, return_logit=False):
   """Both heads over n pairs, batched to bound the size of the materialised delta tensor.
-  Returns (overlap (n,) f32, yaw (n,) int64, corr (n, 360) float64/32 numpy)."""
+  Returns (overlap (n,) f32, yaw (n,) int64, corr (n, 360) float64/32 numpy[, logit (n,)])."""
   n = l_fv.shape[0]
-  ov, cr = [], []
+  ov, cr, zs = [], [], []
   for s in range(0, n, batch):
-    ov.append(delta_head(l_fv[s:s + batch], r_fv[s:s + batch], weights, model_cfg, dtype)[:, 0])
+    _, z, o = delta_head(l_fv[s:s + batch], r_fv[s:s + batch], weights, model_cfg, dtype, return_all=True)
+    ov.append(o[:, 0].astype(np.float32))
+    zs.append(z[:, 0])
     cr.append(correlation_head(l_fv[s:s + batch], r_fv[s:s + batch], dtype))
   overlap = np.concatenate(ov) if ov else np.zeros((0,), np.float32)
   corr = np.concatenate(cr) if cr else np.zeros((0, l_fv.shape[2]))
   o, yaw = readout(overlap, corr)
+  if return_logit:
+    return o, yaw, corr, (np.concatenate(zs) if zs else np.zeros((0,)))
   return o, yaw, corr
+
+
+def spread_dense(weights, logits, target_std=1.5):
+  """Test helper: rescale / recentre the Dense(1) layer so that the given raw logits map to
+  overlaps spread over (0,1) -- a much stricter check of an absolute 1e-3 gate than Glorot's
+  near-constant 0.5.  Dense is linear: new logit = g * (raw - median(raw))."""
+  k, b = weights['overlap_output']
+  raw = np.asarray(logits, np.float64) - float(b[0])
+  g = target_std / max(float(np.std(raw)), 1e-12)
+  med = float(np.median(raw))
+  w2 = dict(weights)
+  w2['overlap_output'] = ((k.astype(np.float64) * g).astype(np.float32), np.array([-g * med], np.float32))
+  return w2
 
 
 # ----------------------------------------------------------------------------------------------

@@ -1,0 +1,143 @@
+"""GPU parity of the leg and the two heads through the C ABI against the float64 oracle
+(parity unpinned by the reference, see oracle/network.py): overlap within 1e-3 (the tolerance
+BASELINE.json's north_star states), yaw equal except on near-ties of the oracle's own scores."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import network as N
+from overlapnet_b200 import synth
+from overlapnet_b200.engine import Engine
+
+pytestmark = pytest.mark.gpu
+
+MODEL = {'additional_unsymmetric_layer3a': True, 'strides_layer1': [2, 2]}
+OVERLAP_TOL = 1e-3          # BASELINE.json north_star: "overlap/yaw floats within 1e-3"
+YAW_TIE_REL = 2e-4          # a yaw flip is accepted only if the oracle's two scores differ by less
+
+
+def check_yaw(yaw_gpu, yaw_ref, corr_ref):
+  bad = []
+  for p in range(len(yaw_ref)):
+    if int(yaw_gpu[p]) != int(yaw_ref[p]):
+      kg, kr = 180 - int(yaw_gpu[p]), 180 - int(yaw_ref[p])
+      gap = corr_ref[p, kr] - corr_ref[p, kg]
+      if gap > YAW_TIE_REL * np.abs(corr_ref[p]).max():
+        bad.append((p, int(yaw_gpu[p]), int(yaw_ref[p]), float(gap)))
+  assert not bad, bad
+
+
+@pytest.fixture(scope='module')
+def setup():
+  w = N.glorot_weights(4, MODEL, seed=0)
+  x = synth.range_like_images(1234, 6, 4)
+  fv_ref = N.leg_forward(x, w, MODEL)                     # float64 oracle -> float32 (6,1,360,128)
+  return w, x, fv_ref
+
+
+@pytest.mark.parametrize('prec,leg_tol', [('fp32', 2e-5), ('f16_tc', 4e-3)])
+def test_leg_matches_oracle(setup, prec, leg_tol):
+  w, x, fv_ref = setup
+  eng = Engine(model=MODEL, precision=prec, max_batch_scans=4, max_batch_pairs=16)
+  eng.load_weights(w)
+  fv = eng.leg(torch.from_numpy(x).to(eng.device)).cpu().numpy()      # 6 scans > max_batch_scans=4
+  ref = fv_ref[:, 0]
+  err = np.abs(fv - ref).max() / np.abs(ref).max()
+  assert err <= leg_tol, err
+  assert (fv >= 0).all()
+  eng.close()
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'f16_tc'])
+def test_heads_match_oracle(setup, prec):
+  w, x, fv_ref = setup
+  eng = Engine(model=MODEL, precision=prec, max_batch_scans=4, max_batch_pairs=4)
+  eng.load_weights(w)
+  bank_np = fv_ref[:, 0].copy()
+  # strongly related pairs: LEFT = roll(RIGHT, 37) (+ noise) => yaw = -37 (R = roll(L, s) => yaw = s)
+  rng = np.random.default_rng(5)
+  bank_np[1] = np.roll(bank_np[5], 37, axis=0) + np.abs(rng.normal(0, 0.01, bank_np[5].shape)).astype(np.float32)
+  bank_np[2] = np.roll(bank_np[5], -120, axis=0)
+  bank = torch.from_numpy(bank_np).to(eng.device)
+  left = np.array([0, 1, 2, 3, 4, 5, 5, 2], np.int32)          # 8 pairs > max_batch_pairs=4
+  right = np.array([5, 5, 5, 5, 5, 5, 0, 1], np.int32)
+  # rescale the Dense layer so the overlaps of these 8 pairs spread over (0,1): strict 1e-3 check
+  _, _, _, z0 = N.heads_forward(bank_np[left][:, None], bank_np[right][:, None], w, MODEL, batch=2, return_logit=True)
+  w = N.spread_dense(w, z0)
+  eng.load_weights(w)
+  ov_ref, yaw_ref, corr_ref = N.heads_forward(bank_np[left][:, None], bank_np[right][:, None], w, MODEL, batch=2)
+  ov, yaw, corr = eng.heads(bank, torch.from_numpy(left), torch.from_numpy(right), want_corr=True)
+  ov, yaw, corr = ov.cpu().numpy(), yaw.cpu().numpy(), corr.cpu().numpy()
+  assert np.abs(ov - ov_ref).max() <= OVERLAP_TOL, (ov, ov_ref)
+  assert ov_ref.max() - ov_ref.min() > 0.3                      # the test is not degenerate
+  check_yaw(yaw, yaw_ref, corr_ref)
+  assert yaw_ref[1] == -37 and yaw[1] == -37 and yaw[2] == 120 and yaw[5] == 0 and yaw[7] == 157
+  rel = np.abs(corr - corr_ref).max() / np.abs(corr_ref).max()
+  assert rel <= (1e-5 if prec == 'fp32' else 2e-3), rel
+  # 1-vs-N entry point == pair list with RIGHT fixed
+  ov1, yaw1, _ = eng.heads_1vsN(bank, bank[5], cand_idx=torch.tensor([0, 1, 2, 3, 4, 5], dtype=torch.int32))
+  assert np.array_equal(ov1.cpu().numpy(), ov[:6]) and np.array_equal(yaw1.cpu().numpy(), yaw[:6])
+  ov2, yaw2, _ = eng.heads_1vsN(bank, bank[5], n_cand=6)
+  assert np.array_equal(ov2.cpu().numpy(), ov[:6]) and np.array_equal(yaw2.cpu().numpy(), yaw[:6])
+  eng.close()
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'f16_tc'])
+def test_yaw_shift_known_answer(prec):
+  """KAT of the correlation head (NormalizedCorrelation2D.py:112-144):
+  R = roll(L, s) along the width  =>  yaw = s  for every s in [-179, 180]."""
+  w = N.glorot_weights(4, MODEL, seed=1)
+  eng = Engine(model=MODEL, precision=prec, max_batch_scans=1, max_batch_pairs=512)
+  eng.load_weights(w)
+  base = synth.feature_volumes(3, 1)[0, 0]                       # (360,128), non-negative
+  shifts = np.arange(-179, 181)
+  bank_np = np.stack([base] + [np.roll(base, s, axis=0) for s in shifts])
+  bank = torch.from_numpy(bank_np).to(eng.device)
+  n = len(shifts)
+  left = torch.zeros(n, dtype=torch.int32)                       # LEFT = base
+  right = torch.arange(1, n + 1, dtype=torch.int32)              # RIGHT = rolled
+  _, yaw, _ = eng.heads(bank, left, right)
+  assert np.array_equal(yaw.cpu().numpy(), shifts)
+  eng.close()
+
+
+@pytest.mark.parametrize('channels,use', [(5, {'use_intensity': True}),
+                                          (25, {'use_intensity': True, 'use_class_probabilities': True})])
+def test_leg_other_channel_counts(channels, use):
+  w = N.glorot_weights(channels, MODEL, seed=2)
+  x = synth.range_like_images(7, 2, channels)
+  ref = N.leg_forward(x, w, MODEL)[:, 0]
+  for prec, tol in (('fp32', 2e-5), ('f16_tc', 4e-3)):
+    eng = Engine(use=use, model=MODEL, precision=prec, max_batch_scans=2, max_batch_pairs=1)
+    assert eng.C == channels
+    eng.load_weights(w)
+    fv = eng.leg(torch.from_numpy(x).to(eng.device)).cpu().numpy()
+    assert np.abs(fv - ref).max() / np.abs(ref).max() <= tol
+    eng.close()
+
+
+def test_full_size_1xN_properties():
+  """BASELINE config 2 size (1 query x 1101 candidates) through the product path: results are
+  independent of candidate order / chunking, equal to the pairwise entry point, and the query
+  against itself gives yaw 0."""
+  w = N.glorot_weights(4, MODEL, seed=0)
+  eng = Engine(model=MODEL, precision='f16_tc', max_batch_scans=1, max_batch_pairs=1101)
+  n = 1101
+  bank_np = synth.feature_volumes(11, n)[:, 0] * np.float32(0.2)
+  sel = np.array([0, 17, 500, 1100])
+  _, _, _, z0 = N.heads_forward(bank_np[sel][:, None], np.repeat(bank_np[17][None, None], 4, 0), w, MODEL, return_logit=True)
+  w = N.spread_dense(w, z0)
+  eng.load_weights(w)
+  bank = torch.from_numpy(bank_np).to(eng.device)
+  q = bank[17].clone()
+  ov, yaw, _ = eng.heads_1vsN(bank, q, n_cand=n)
+  perm = torch.randperm(n, generator=torch.Generator().manual_seed(0)).to(torch.int32)
+  ovp, yawp, _ = eng.heads_1vsN(bank, q, cand_idx=perm)
+  assert torch.equal(ov[perm.long().to(eng.device)], ovp) and torch.equal(yaw[perm.long().to(eng.device)], yawp)
+  assert int(yaw[17]) == 0
+  assert torch.isfinite(ov).all() and (ov >= 0).all() and (ov <= 1).all()
+  # spot-check 4 of the 1101 against the float64 oracle
+  ov_ref, yaw_ref, corr_ref = N.heads_forward(bank_np[sel][:, None], np.repeat(bank_np[17][None, None], 4, 0), w, MODEL)
+  assert np.abs(ov.cpu().numpy()[sel] - ov_ref).max() <= OVERLAP_TOL
+  check_yaw(yaw.cpu().numpy()[sel], yaw_ref, corr_ref)
+  eng.close()
