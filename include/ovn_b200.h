@@ -90,6 +90,13 @@ int         ovn_feature_channels(const ovn_handle* h);      /* 128 */
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t     ovn_launch_count(const ovn_handle* h);
 
+/* ---- per-kernel device timing (bench.py roofline): CUDA events recorded around the named kernels
+ * on the launching stream while enabled.  ovn_profile_read synchronises the device, returns the
+ * accumulated milliseconds / launch count since the last read and resets them.  Names:
+ * "delta_conv1", "conv2", "conv3", "corr", "project_scatter", "project_gather", "leg". */
+int ovn_profile_enable(ovn_handle* h, int on);
+int ovn_profile_read(ovn_handle* h, const char* kernel, double* total_ms, int64_t* launches);
+
 /* ---- weights: replaces load_weights(by_name=True), infer.py:117-120 ----------------------- */
 /* kernel: Keras layout, conv (kh,kw,cin,cout) / dense (in,out), float32 host memory; bias (cout).
  * Layer names: s_conv1..s_conv10 (+s_conv3a), c_conv1..c_conv3, overlap_output

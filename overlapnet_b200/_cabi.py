@@ -14,7 +14,7 @@ PREC_F16_TC = 1
 SYMBOLS = [
     'ovn_default_config', 'ovn_create', 'ovn_destroy', 'ovn_last_error', 'ovn_status_string',
     'ovn_abi_version', 'ovn_input_channels', 'ovn_feature_width', 'ovn_feature_channels',
-    'ovn_launch_count', 'ovn_set_weights', 'ovn_finalize_weights', 'ovn_project_batch',
+    'ovn_launch_count', 'ovn_profile_enable', 'ovn_profile_read', 'ovn_set_weights', 'ovn_finalize_weights', 'ovn_project_batch',
     'ovn_normals_batch', 'ovn_semantic_batch', 'ovn_preprocess_batch', 'ovn_pack_input',
     'ovn_leg_forward', 'ovn_heads_forward', 'ovn_heads_1vsN', 'ovn_encode_clouds_host',
     'ovn_query_cloud_vs_bank_host',
@@ -67,6 +67,8 @@ def lib():
     getattr(L, f).argtypes = [vp]
   L.ovn_launch_count.argtypes = [vp]
   L.ovn_launch_count.restype = i64
+  L.ovn_profile_enable.argtypes = [vp, C.c_int]
+  L.ovn_profile_read.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(i64)]
   L.ovn_set_weights.argtypes = [vp, C.c_char_p, vp, C.POINTER(i64), i32, vp, i64]
   L.ovn_finalize_weights.argtypes = [vp]
   L.ovn_project_batch.argtypes = [vp, vp, vp, i32, i64, f32, vp, vp, vp, vp, vp]

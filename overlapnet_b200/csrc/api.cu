@@ -172,10 +172,10 @@ int ovn_create(const ovn_config* cfg, ovn_handle** out) {
   CREATE_CUDA(cudaMalloc(&h->d_query_fv, (size_t)Wf * kFeatC * sizeof(float)));
   CREATE_CUDA(cudaMalloc(&h->d_idx_tmp, (size_t)2 * c.max_batch_pairs * sizeof(int32_t)));
   CREATE_CUDA(cudaMalloc(&h->d_logit, (size_t)c.max_batch_pairs * sizeof(float)));
+  if (h->net_ok) CREATE_CUDA(cudaMalloc(&h->d_G, (size_t)c.max_batch_pairs * Wf * Wf * sizeof(float)));
   if (c.precision == OVN_PREC_FP32 && h->net_ok) {
     CREATE_CUDA(cudaMalloc(&h->d_o1, (size_t)c.max_batch_pairs * h->o1_h * h->o1_w * 64 * sizeof(float)));
     CREATE_CUDA(cudaMalloc(&h->d_o2, (size_t)c.max_batch_pairs * h->o2_h * h->o2_w * 128 * sizeof(float)));
-    CREATE_CUDA(cudaMalloc(&h->d_G, (size_t)c.max_batch_pairs * Wf * Wf * sizeof(float)));
   } else if (c.precision != OVN_PREC_F16_TC && c.precision != OVN_PREC_FP32) {
     CREATE_FAIL(OVN_ERR_BAD_CONFIG, "ovn_create: unknown precision %d", c.precision);
   }
@@ -196,7 +196,37 @@ int ovn_destroy(ovn_handle* h) {
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  for (auto& v : h->prof_ev) for (cudaEvent_t e : v) cudaEventDestroy(e);
   delete h;
+  return OVN_OK;
+}
+
+int ovn_profile_enable(ovn_handle* h, int on) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  h->profiling = on != 0;
+  return OVN_OK;
+}
+
+int ovn_profile_read(ovn_handle* h, const char* kernel, double* total_ms, int64_t* launches) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  if (!kernel || !total_ms || !launches) OVN_SET_ERR(h, OVN_ERR_INVALID_ARG, "ovn_profile_read: NULL argument");
+  static const char* names[kProfKinds] = {"delta_conv1", "conv2", "conv3", "corr", "project_scatter",
+                                          "project_gather", "leg"};
+  int kind = -1;
+  for (int i = 0; i < kProfKinds; ++i) if (strcmp(kernel, names[i]) == 0) kind = i;
+  if (kind < 0) OVN_SET_ERR(h, OVN_ERR_INVALID_ARG, "ovn_profile_read: unknown kernel '%s'", kernel);
+  OVN_CUDA(h, cudaDeviceSynchronize());
+  std::vector<cudaEvent_t>& ev = h->prof_ev[kind];
+  double ms = 0;
+  int64_t n = 0;
+  for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, ev[i], ev[i + 1]) == cudaSuccess) { ms += t; ++n; }
+  }
+  for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  ev.clear();
+  *total_ms = ms;
+  *launches = n;
   return OVN_OK;
 }
 

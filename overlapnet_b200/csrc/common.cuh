@@ -14,6 +14,7 @@ namespace ovn {
 
 constexpr int kFeatC = 128;           // leg output channels (generateNet.py:214)
 constexpr int kMaxLegLayers = 12;
+enum ProfKind { PROF_DELTA = 0, PROF_CONV2, PROF_CONV3, PROF_CORR, PROF_SCATTER, PROF_GATHER, PROF_LEG, kProfKinds };
 
 struct ConvSpec {                      // one Conv2D layer (valid padding, bias)
   char name[24];
@@ -30,6 +31,8 @@ struct LayerWeights {
 };
 
 }  // namespace ovn
+
+namespace ovn { struct TcState; }
 
 struct ovn_handle {
   ovn_config cfg;
@@ -79,6 +82,10 @@ struct ovn_handle {
   void* h_pinned = nullptr;                  // pinned staging for host entry points
   int64_t cap_pinned = 0;
   cudaStream_t own_stream = nullptr;
+  // per-kernel profiling (ovn_profile_enable / ovn_profile_read)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_ev[ovn::kProfKinds];   // start/stop pairs, in launch order
+  ovn::TcState* tc = nullptr;              // tensor-core path state (network_tc.cu)
 };
 
 #define OVN_SET_ERR(h, code, ...)                                 \
@@ -110,6 +117,15 @@ struct ovn_handle {
 
 namespace ovn {
 
+// RAII-free profiling helpers: record an event on `s` before / after a launch when enabled
+inline void prof_mark(ovn_handle* h, int kind, cudaStream_t s) {
+  if (!h->profiling) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, s);
+  h->prof_ev[kind].push_back(e);
+}
+
 // ---- stage entry points implemented in the .cu files (called from api.cu) -------------------
 int project_batch(ovn_handle* h, const float* d_points, const int64_t* d_offsets, int n_scans,
                   int64_t n_total, float max_range, float* d_range, float* d_vertex,
@@ -128,6 +144,9 @@ int leg_forward_fp32(ovn_handle* h, const float* d_input, int n, float* d_fv, cu
 int heads_forward_fp32(ovn_handle* h, const float* d_bank, const float* d_query,
                        const int32_t* d_left, const int32_t* d_right, int n, float* d_overlap,
                        int32_t* d_yaw, float* d_corr, cudaStream_t s);
+
+int corr_forward_fp32(ovn_handle* h, const float* d_bank, const float* d_query, const int32_t* left,
+                      const int32_t* right, int np, int32_t* d_yaw, float* d_corr, cudaStream_t s);
 
 int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cudaStream_t s);
 int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query,

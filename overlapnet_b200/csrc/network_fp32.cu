@@ -226,6 +226,7 @@ k_corr_readout(const float* __restrict__ G, int Wf, float* __restrict__ corr_out
 // ---- drivers ----------------------------------------------------------------------------------
 int leg_forward_fp32(ovn_handle* h, const float* d_input, int n, float* d_fv, cudaStream_t s) {
   const float* x = d_input;
+  prof_mark(h, PROF_LEG, s);
   for (int l = 0; l < h->n_leg; ++l) {
     const ConvSpec& L = h->leg[l];
     float* y = (l == h->n_leg - 1) ? d_fv : h->d_act[l & 1];
@@ -235,6 +236,21 @@ int leg_forward_fp32(ovn_handle* h, const float* d_input, int n, float* d_fv, cu
     if (rc != OVN_OK) return rc;
     x = y;
   }
+  prof_mark(h, PROF_LEG, s);
+  return OVN_OK;
+}
+
+// correlation head for <= max_batch_pairs pairs: Gram matrix per pair (fp32), then circular
+// diagonal sums + argmax.  LEFT = bank[left[p]], RIGHT = query or bank[right[p]].
+int corr_forward_fp32(ovn_handle* h, const float* d_bank, const float* d_query, const int32_t* left,
+                      const int32_t* right, int np, int32_t* d_yaw, float* d_corr, cudaStream_t s) {
+  const int Wf = h->cfg.leg_output_width, Cf = kFeatC;
+  GramOperand a{d_bank, left, Wf, Cf};
+  BOperand b{d_bank, d_query, right, (int64_t)Wf * Cf, 1};
+  int rc = launch_gemm(h, a, b, nullptr, h->d_G, Wf, Wf, Cf, np, 0, s);
+  if (rc != OVN_OK) return rc;
+  k_corr_readout<<<np, 384, Wf * sizeof(float), s>>>(h->d_G, Wf, d_corr, d_yaw);
+  OVN_LAUNCH_CHECK(h);
   return OVN_OK;
 }
 
@@ -252,8 +268,10 @@ int heads_forward_fp32(ovn_handle* h, const float* d_bank, const float* d_query,
     {
       DeltaOperand a{d_bank, d_query, left, right, Wf, Cf, sz, h->o1_w};
       BOperand b{h->d_w[base + 0], nullptr, nullptr, 0, 0};
+      prof_mark(h, PROF_DELTA, s);
       int rc = launch_gemm(h, a, b, h->d_b[base + 0], h->d_o1, np * h->o1_h * h->o1_w, h->head[0].cout,
                            sz * Cf, 1, 0, s);
+      prof_mark(h, PROF_DELTA, s);
       if (rc != OVN_OK) return rc;
     }
     // c_conv2 (relu): (15,1) stride (15,1) over [p][360][24][64]
@@ -277,15 +295,10 @@ int heads_forward_fp32(ovn_handle* h, const float* d_bank, const float* d_query,
     }
     k_dense_sigmoid<<<np, 256, 0, s>>>(d_o3, h->d_w[base + 3], h->d_b[base + 3], h->dense_in, d_overlap + p0);
     OVN_LAUNCH_CHECK(h);
-    // correlation head: Gram matrix per pair, then circular diagonal sums + argmax
     {
-      GramOperand a{d_bank, left, Wf, Cf};
-      BOperand b{d_bank, d_query, right, (int64_t)Wf * Cf, 1};
-      int rc = launch_gemm(h, a, b, nullptr, h->d_G, Wf, Wf, Cf, np, 0, s);
+      int rc = corr_forward_fp32(h, d_bank, d_query, left, right, np, d_yaw + p0,
+                                 d_corr ? d_corr + (int64_t)p0 * Wf : nullptr, s);
       if (rc != OVN_OK) return rc;
-      k_corr_readout<<<np, 384, Wf * sizeof(float), s>>>(h->d_G, Wf, d_corr ? d_corr + (int64_t)p0 * Wf : nullptr,
-                                                         d_yaw + p0);
-      OVN_LAUNCH_CHECK(h);
     }
   }
   return OVN_OK;

@@ -437,9 +437,11 @@ static int run_projection(ovn_handle* h, const float* d_points, const int64_t* d
   }
   if (n_total > 0) {
     const int64_t blocks = (n_total + 255) / 256;
+    prof_mark(h, PROF_SCATTER, s);
     k_project_scatter<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(d_points), d_offsets,
                                                        n_scans, n_total, P, h->d_keys,
                                                        need_rank ? h->d_valid_words : nullptr);
+    prof_mark(h, PROF_SCATTER, s);
     OVN_LAUNCH_CHECK(h);
     if (need_rank) {
       const int nb = (int)((n_words + 1023) / 1024);
@@ -452,8 +454,10 @@ static int run_projection(ovn_handle* h, const float* d_points, const int64_t* d
     }
   }
   dim3 grid((P.W + TILE_C - 1) / TILE_C, (P.H + TILE_R - 1) / TILE_R, n_scans);
+  prof_mark(h, PROF_GATHER, s);
   k_project_gather<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(d_points), d_offsets, P, h->d_keys,
                                         h->d_valid_words, h->d_word_prefix, out);
+  prof_mark(h, PROF_GATHER, s);
   OVN_LAUNCH_CHECK(h);
   return OVN_OK;
 }

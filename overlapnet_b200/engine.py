@@ -90,6 +90,15 @@ class Engine:
   def launch_count(self):
     return int(lib().ovn_launch_count(self._h))
 
+  def profile_enable(self, on=True):
+    check(self._h, lib().ovn_profile_enable(self._h, int(bool(on))), 'ovn_profile_enable')
+
+  def profile_read(self, kernel):
+    """(total milliseconds, launches) of the named kernel since the last read; synchronises."""
+    ms, n = C.c_double(0), C.c_int64(0)
+    check(self._h, lib().ovn_profile_read(self._h, kernel.encode(), C.byref(ms), C.byref(n)), 'ovn_profile_read')
+    return ms.value, int(n.value)
+
   def load_weights(self, weights):
     """weights: {layer name: (kernel, bias)} in Keras layouts (overlapnet_b200.weights)."""
     L = lib()

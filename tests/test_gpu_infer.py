@@ -1,0 +1,147 @@
+"""The drop-in ``Infer`` class against the oracle's restatement of the reference's call semantics
+(infer.py:124-265): same .npy inputs, same LEFT/RIGHT convention, same return shapes and dtypes,
+same error behaviour."""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+from oracle import network as N
+from oracle import projection as P
+from oracle.infer_ref import InferRef
+from overlapnet_b200 import synth, weights as W
+
+pytestmark = pytest.mark.gpu
+
+MODEL = {'modelType': 'SiameseNetworkTemplate', 'legsType': '360OutputkLegs',
+         'overlap_head': 'DeltaLayerConv1NetworkHead', 'orientation_head': 'CorrelationHead',
+         'inputShape': [64, 900], 'leg_output_width': 360, 'strides_layer1': [2, 2],
+         'additional_unsymmetric_layer3a': True}
+
+
+def check_yaw(yaw_gpu, yaw_ref, corr_ref, rel=2e-4):
+  for p in range(len(yaw_ref)):
+    if int(yaw_gpu[p]) != int(yaw_ref[p]):
+      kg, kr = 180 - int(yaw_gpu[p]), 180 - int(yaw_ref[p])
+      assert corr_ref[p, kr] - corr_ref[p, kg] <= rel * np.abs(corr_ref[p]).max(), (p, yaw_gpu[p], yaw_ref[p])
+
+
+@pytest.fixture(scope='module')
+def dataset(tmp_path_factory):
+  """A preprocessed data folder laid out like the reference's (depth/ normal/ *.npy), generated
+  with the oracle from seeded synthetic clouds, plus seeded weights in the .npz container."""
+  root = tmp_path_factory.mktemp('data')
+  seq = root / '07'
+  (seq / 'depth').mkdir(parents=True)
+  (seq / 'normal').mkdir()
+  base = synth.kitti_like_cloud(900, n_points=60000)
+  for i in range(4):
+    if i < 3:
+      ang = np.deg2rad(25.0 * i)                       # same scene rotated about z: a known yaw
+      c, s = np.cos(ang), np.sin(ang)
+      pts = base.copy()
+      pts[:, 0], pts[:, 1] = c * base[:, 0] - s * base[:, 1], s * base[:, 0] + c * base[:, 1]
+    else:
+      pts = synth.kitti_like_cloud(901, n_points=60000)
+    rng, vert, _, _ = P.range_projection(pts)
+    np.save(str(seq / 'depth' / ('%06d.npy' % i)), rng)
+    np.save(str(seq / 'normal' / ('%06d.npy' % i)), P.gen_normal_map(rng, vert))
+  w = N.glorot_weights(4, MODEL, seed=3)
+  wpath = str(root / 'weights.npz')
+  W.save_npz(wpath, w)
+  cfg = {'pretrained_weightsfilename': wpath, 'use_depth': True, 'use_normals': True,
+         'use_class_probabilities': False, 'use_class_probabilities_pca': False, 'use_intensity': False,
+         'data_root_folder': str(root), 'infer_seqs': '07', 'batch_size': 16, 'model': copy.deepcopy(MODEL)}
+  return cfg, w
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'f16_tc'])
+def test_infer_api_matches_reference_semantics(dataset, prec):
+  from overlapnet_b200.infer import Infer
+  cfg, w = dataset
+  cfg = copy.deepcopy(cfg)
+  inf = Infer(cfg, precision=prec)
+  ref = InferRef(copy.deepcopy(cfg), w)
+  assert cfg['model']['inputShape'] == [64, 900, 4]            # mutated in place like infer.py:76-82
+  assert inf.no_input_channels == 4 and inf.batch_size == 16 and inf.seq == '07'
+
+  # ---- infer_one: LEFT = file2, RIGHT = file1; overlap (1,) f32, yaw (1,) int
+  ov, yaw = inf.infer_one('/any/where/000000.bin', '000001.bin')
+  ov_r, yaw_r, corr_r = ref.infer_one('000000.bin', '000001.bin')
+  assert ov.shape == (1,) and ov.dtype == np.float32 and yaw.shape == (1,) and yaw.dtype.kind == 'i'
+  assert list(inf.filenames) == ['000001', '000000']
+  assert abs(float(ov[0]) - float(ov_r[0])) <= 1e-3
+  check_yaw(yaw, yaw_r, corr_r)
+
+  # ---- create_feature_volumes: (n,1,360,128) float32
+  fv = inf.create_feature_volumes(['000000', '000003'])
+  fv_r = ref.create_feature_volumes(['000000', '000003'])
+  assert fv.shape == (2, 1, 360, 128) and fv.dtype == np.float32
+  assert np.abs(fv - fv_r).max() / np.abs(fv_r).max() <= (2e-5 if prec == 'fp32' else 4e-3)
+
+  # ---- infer_multiple: stateful bank, ids must come 0,1,2,...
+  assert inf.infer_multiple(0, []) is None and ref.infer_multiple(0, []) is None
+  r1 = inf.infer_multiple(1, [0])
+  r1_ref = ref.infer_multiple(1, [0])
+  assert r1[0].shape == () and r1[1].shape == (1,)              # squeeze() of one pair is 0-d (infer.py:197)
+  assert abs(float(r1[0]) - float(r1_ref[0])) <= 1e-3
+  r2 = inf.infer_multiple(2, [0, 1])
+  r2_ref = ref.infer_multiple(2, [0, 1])
+  assert r2[0].shape == (2,) and r2[1].shape == (2,)
+  assert np.abs(r2[0] - r2_ref[0]).max() <= 1e-3
+  check_yaw(r2[1], r2_ref[1], r2_ref[2])
+  assert len(inf.feature_volumes) == 3 and inf.feature_volumes[0].shape == (1, 360, 128)
+
+  # ---- infer_multiple_vs_multiple: LEFT = second_idxs, RIGHT = first_idxs
+  names = ['000000', '000001.bin', '/x/000003.bin']
+  r3 = inf.infer_multiple_vs_multiple(names, [0, 1, 2], [2, 1, 1])
+  r3_ref = ref.infer_multiple_vs_multiple(names, [0, 1, 2], [2, 1, 1])
+  assert np.abs(r3[0] - r3_ref[0]).max() <= 1e-3
+  check_yaw(r3[1], r3_ref[1], r3_ref[2])
+  assert r3[1][1] == 0                                           # a scan against itself
+  assert inf.feature_volumes.shape == (3, 1, 360, 128)
+  assert inf.infer_multiple_vs_multiple(names, [], []) is None
+
+
+def test_infer_error_behaviour(dataset):
+  from overlapnet_b200.infer import Infer
+  cfg, _ = dataset
+  inf = Infer(copy.deepcopy(cfg), precision='fp32')
+  with pytest.raises(Exception, match='only works with .bin files'):
+    inf.infer_one('a.pcd', 'b.bin')
+  with pytest.raises(Exception, match='same size'):
+    inf.infer_multiple_vs_multiple(['000000'], [0, 0], [0])
+  with pytest.raises(Exception, match='Could not read depth image'):
+    inf.create_feature_volumes(['999999'])
+  bad = copy.deepcopy(cfg)
+  bad['infer_seqs'] = 'nope'
+  inf2 = Infer(bad, precision='fp32')
+  with pytest.raises(Exception, match='first generate preprocessed input data'):
+    inf2.infer_one('000000.bin', '000001.bin')
+  worse = copy.deepcopy(cfg)
+  worse['model']['legsType'] = 'NoSuchLegs'
+  with pytest.raises(AttributeError):
+    Infer(worse)
+  missing = copy.deepcopy(cfg)
+  del missing['use_depth']
+  with pytest.raises(KeyError):                                  # infer.py:63 reads it unguarded
+    Infer(missing)
+
+
+def test_infer_raw_cloud_extension(dataset, tmp_path):
+  """Extension: raw .bin scans through the fused projection kernels give the same answer as the
+  .npy round trip of the reference flow."""
+  from overlapnet_b200.infer import Infer
+  cfg, _ = dataset
+  inf = Infer(copy.deepcopy(cfg), precision='fp32')
+  base = synth.kitti_like_cloud(900, n_points=60000)
+  ang = np.deg2rad(25.0)
+  rot = base.copy()
+  rot[:, 0] = np.cos(ang) * base[:, 0] - np.sin(ang) * base[:, 1]
+  rot[:, 1] = np.sin(ang) * base[:, 0] + np.cos(ang) * base[:, 1]
+  base.tofile(str(tmp_path / '000000.bin'))
+  rot.tofile(str(tmp_path / '000001.bin'))
+  ov_raw, yaw_raw = inf.infer_one_raw(str(tmp_path / '000000.bin'), str(tmp_path / '000001.bin'))
+  ov_npy, yaw_npy = inf.infer_one('000000.bin', '000001.bin')
+  assert np.array_equal(ov_raw, ov_npy) and np.array_equal(yaw_raw, yaw_npy)
