@@ -181,8 +181,10 @@ def main():
   # ---- candidate bank of this rank: 32 synthetic scans encoded by the product path, yaw-rolled to 1101
   clouds = [synth.kitti_like_cloud(1000 * rank + s) for s in range(N_SRC_SCANS)]
   fv_src = eng.leg(eng.preprocess(eng.upload_clouds(clouds)))
-  rolls = [(i // N_SRC_SCANS) * 10 for i in range(N_CAND)]
-  bank = torch.stack([torch.roll(fv_src[i % N_SRC_SCANS], rolls[i], dims=0) for i in range(N_CAND)]).contiguous()
+  src = torch.arange(N_CAND, device=dev) % N_SRC_SCANS
+  roll = (torch.arange(N_CAND, device=dev) // N_SRC_SCANS) * 10
+  rows = (torch.arange(eng.Wf, device=dev)[None, :] - roll[:, None]) % eng.Wf          # one gather, no per-row kernels
+  bank = fv_src[src[:, None], rows].contiguous()
   del fv_src
 
   # ---- query clouds: a fresh scan per step (pinned host copies for the e2e leg)

@@ -141,6 +141,7 @@ int pack_input(ovn_handle* h, const float* d_depth, const float* d_normal, const
                const float* d_intensity, int n_scans, float* d_input, cudaStream_t s);
 
 int leg_forward_fp32(ovn_handle* h, const float* d_input, int n, float* d_fv, cudaStream_t s);
+int leg_layer_fp32(ovn_handle* h, int l, const float* x, float* y, int n, cudaStream_t s);
 int heads_forward_fp32(ovn_handle* h, const float* d_bank, const float* d_query,
                        const int32_t* d_left, const int32_t* d_right, int n, float* d_overlap,
                        int32_t* d_yaw, float* d_corr, cudaStream_t s);

@@ -224,6 +224,13 @@ k_corr_readout(const float* __restrict__ G, int Wf, float* __restrict__ corr_out
 }
 
 // ---- drivers ----------------------------------------------------------------------------------
+int leg_layer_fp32(ovn_handle* h, int l, const float* x, float* y, int n, cudaStream_t s) {
+  const ConvSpec& L = h->leg[l];
+  ConvOperand a{x, L.h_in, L.w_in, L.cin, L.kw, L.sh, L.sw, L.h_out, L.w_out};
+  BOperand b{h->d_w[l], nullptr, nullptr, 0, 0};
+  return launch_gemm(h, a, b, h->d_b[l], y, n * L.h_out * L.w_out, L.cout, L.kh * L.kw * L.cin, 1, L.relu, s);
+}
+
 int leg_forward_fp32(ovn_handle* h, const float* d_input, int n, float* d_fv, cudaStream_t s) {
   const float* x = d_input;
   prof_mark(h, PROF_LEG, s);

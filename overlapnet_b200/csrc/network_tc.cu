@@ -39,18 +39,29 @@ constexpr int S15 = 15;
 constexpr int NB = 24;                  // 360 / 15
 constexpr int PAIR_ROWS = NB * NB;      // 576 rows of c_conv2 output per pair
 constexpr long long kWaitCycles = 1ll << 28;
+constexpr int K4_PITCH = CF + 8;        // fp16 row pitch of L / R for k_delta_conv1_tc: 272 B => conflict-free LDS.128 across rows
 
 struct TcState {
   __half* w1p = nullptr;        // [60 steps][4][64][8]
   __half* w2p = nullptr;        // [30 slabs][4][128][8]
   __half* w3p = nullptr;        // [2 halves][36 slabs][4][128][8]
-  int* slab2_plane = nullptr; int* slab2_shift = nullptr;
+  int* slab2_plane = nullptr; int* slab2_shift = nullptr;     // per-copy (n_slabs*4) tables
   int* slab3_plane = nullptr; int* slab3_shift = nullptr;
+  // tensor-core leg (layers 2..): packed weights + copy tables per layer, ping-pong activation planes
+  __half* wleg[kMaxLegLayers] = {};
+  int* leg_plane[kMaxLegLayers] = {};
+  int* leg_shift[kMaxLegLayers] = {};
+  int leg_slabs[kMaxLegLayers] = {};
+  int leg_nt[kMaxLegLayers] = {};
+  __half* actp[2] = {nullptr, nullptr};
   __half* l16 = nullptr;        // [max_pairs][360][128]
   __half* r16 = nullptr;        // [max_pairs][360][128] (pair mode) / [1][360][128] (query mode)
   __half* o1 = nullptr;         // [120 planes][rows_pad][8]
   __half* x3 = nullptr;         // [16 planes][rows_pad][8]
   float* partial = nullptr;     // [rows_pad][2]
+  __half* lc = nullptr;         // correlation operands: [max_pairs][3 tiles][2 k-halves][hi,lo][8][128][8]
+  __half* rc = nullptr;         // [max_pairs or 1][2 n-halves][hi,lo][16][192][8]
+  float* corr_part = nullptr;   // [max_pairs][2][360]
   int* d_err = nullptr;
   int64_t rows_pad = 0;
 };
@@ -71,14 +82,16 @@ k_gather_rows_f16(const float* __restrict__ bank, const int32_t* __restrict__ id
   uint2 o;
   o.x = *reinterpret_cast<uint32_t*>(&a);
   o.y = *reinterpret_cast<uint32_t*>(&b);
-  reinterpret_cast<uint2*>(out + (int64_t)p * WF * CF)[e] = o;
+  const int64_t r = e / (CF / 4), c4 = e % (CF / 4);           // padded row pitch (K4_PITCH halves)
+  reinterpret_cast<uint2*>(out + ((int64_t)p * WF + r) * K4_PITCH)[c4] = o;
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_delta_conv1_tc
 // ------------------------------------------------------------------------------------------------
 constexpr int K4_THREADS = 512;
-constexpr int K4_STAGES = 6;
+constexpr int K4_STAGES = 6;            // A ring: TMEM column slots
+constexpr int K4_BSLOTS = 24;           // B ring: shared-memory slots of W1 slices (decoupled, deep enough for L2 latency)
 constexpr int K4_TILES = 3;
 constexpr int K4_ACOL0 = 192;           // TMEM columns: D = [0,192), A stages = [192, 192 + 6*48)
 constexpr int K4_STAGE_COLS = 48;
@@ -86,12 +99,11 @@ constexpr int K4_STEPS = 60;            // 4 channel chunks x 15 dj per jb
 constexpr int K4_BSLICE = 4096;         // bytes of W1 per step: [4 k8][64 o][8]
 
 struct K4Smem {
-  __half R[WF * CF];
-  __half L[WF * CF];
-  __half B[K4_STAGES][K4_BSLICE / 2];
+  __half R[WF * K4_PITCH];
+  __half B[K4_BSLOTS][K4_BSLICE / 2];
   float bias[64];
-  uint64_t a_full[K4_STAGES], b_full[K4_STAGES], empty[K4_STAGES];
-  uint64_t d_full, d_empty, l_full, l_empty, r_full;
+  uint64_t a_full[K4_STAGES], a_empty[K4_STAGES], b_full[K4_BSLOTS], b_empty[K4_BSLOTS];
+  uint64_t d_full, d_empty, r_full, r_empty;
   uint32_t tmem_base;
 };
 
@@ -101,6 +113,10 @@ struct K4Smem {
     goto done;                                           \
   }
 
+// Measured on B200 (profiles/r1_*): with W1 slices sharing the 6-deep A ring the kernel was bound
+// by the L2 -> shared round trip of a slice (slot turnaround ~4000 clk); the W1 ring is therefore
+// separate and 24 deep, which needs the LEFT volume out of shared memory: producers read their
+// three LEFT rows' 16 channels straight from L2 into registers one (jb, chunk) ahead.
 __global__ void __launch_bounds__(K4_THREADS, 1)
 k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16, int r_per_pair,
                  const __half* __restrict__ W1p, const float* __restrict__ bias1, __half* __restrict__ o1,
@@ -110,9 +126,10 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int s = 0; s < K4_STAGES; ++s) { mbar_init(&S.a_full[s], 8); mbar_init(&S.b_full[s], 1); mbar_init(&S.empty[s], 1); }
+    for (int s = 0; s < K4_STAGES; ++s) { mbar_init(&S.a_full[s], 8); mbar_init(&S.a_empty[s], 1); }
+    for (int s = 0; s < K4_BSLOTS; ++s) { mbar_init(&S.b_full[s], 1); mbar_init(&S.b_empty[s], 1); }
     mbar_init(&S.d_full, 1); mbar_init(&S.d_empty, 4);
-    mbar_init(&S.l_full, 1); mbar_init(&S.l_empty, 8); mbar_init(&S.r_full, 1);
+    mbar_init(&S.r_full, 1); mbar_init(&S.r_empty, 8);
     mbar_fence_init();
   }
   if (tid < 64) S.bias[tid] = bias1[tid];
@@ -121,58 +138,75 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = S.tmem_base;
-  constexpr uint32_t VOL_BYTES = WF * CF * 2;
+  constexpr uint32_t VOL_BYTES = WF * K4_PITCH * 2;
 
   if (warp == 0) {
-    // ===================== loader: L (and R) per pair, W1 slices per step =====================
+    // ===================== loader: R once (or per pair), W1 slices through the deep ring =======
     if (lane == 0) {
       if (!r_per_pair) {
         mbar_arrive_expect_tx(&S.r_full, VOL_BYTES);
         bulk_g2s(S.R, R16, VOL_BYTES, &S.r_full);
       }
-      uint32_t it = 0, pi = 0;
+      uint32_t pi = 0, bs = 0, bph = 0;
       for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++pi) {
-        TC_WAIT(&S.l_empty, (pi & 1) ^ 1, 101);
-        mbar_arrive_expect_tx(&S.l_full, r_per_pair ? 2 * VOL_BYTES : VOL_BYTES);
-        bulk_g2s(S.L, L16 + (size_t)p * WF * CF, VOL_BYTES, &S.l_full);
-        if (r_per_pair) bulk_g2s(S.R, R16 + (size_t)p * WF * CF, VOL_BYTES, &S.l_full);
+        if (r_per_pair) {
+          TC_WAIT(&S.r_empty, (pi & 1) ^ 1, 101);
+          mbar_arrive_expect_tx(&S.r_full, VOL_BYTES);
+          bulk_g2s(S.R, R16 + (size_t)p * WF * K4_PITCH, VOL_BYTES, &S.r_full);
+        }
         for (int jb = 0; jb < NB; ++jb) {
-          for (int st = 0; st < K4_STEPS; ++st, ++it) {
-            const uint32_t s = it % K4_STAGES, ph = (it / K4_STAGES) & 1;
-            TC_WAIT(&S.empty[s], ph ^ 1, 102);
-            mbar_arrive_expect_tx(&S.b_full[s], K4_BSLICE);
-            bulk_g2s(S.B[s], W1p + (size_t)st * (K4_BSLICE / 2), K4_BSLICE, &S.b_full[s]);
+          for (int st = 0; st < K4_STEPS; ++st) {
+            TC_WAIT(&S.b_empty[bs], bph ^ 1, 102);
+            mbar_arrive_expect_tx(&S.b_full[bs], K4_BSLICE);
+            bulk_g2s(S.B[bs], W1p + (size_t)st * (K4_BSLICE / 2), K4_BSLICE, &S.b_full[bs]);
+            if (++bs == K4_BSLOTS) { bs = 0; bph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) ============================================
-    if (lane == 0) {
+    // ===================== MMA issuer ==========================================================
+    // Warp-uniform loop (addresses / descriptors stay in uniform registers), one elected lane
+    // issues.  The A ring is unrolled (60 steps = 10 x 6 slots: slot offsets are immediates and the
+    // phase is the parity of the outer counter); the B slot is a running counter.
+    {
       const uint32_t idesc = make_idesc_f16(128, 64);
-      uint32_t it = 0, jbit = 0;
+      const uint64_t bdesc0 = make_desc_kmajor_noswizzle(smem_u32(S.B[0]), 1024, 128);
+      const uint32_t bd_hi = (uint32_t)(bdesc0 >> 32), bd_lo = (uint32_t)bdesc0;
+      const bool leader = elect_one() != 0;
+      uint32_t jbit = 0, bs = 0, bph = 0;
       for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
         for (int jb = 0; jb < NB; ++jb, ++jbit) {
           TC_WAIT(&S.d_empty, (jbit & 1) ^ 1, 201);
           fence_after_sync();
-          for (int st = 0; st < K4_STEPS; ++st, ++it) {
-            const uint32_t s = it % K4_STAGES, ph = (it / K4_STAGES) & 1;
-            TC_WAIT(&S.a_full[s], ph, 202);
-            TC_WAIT(&S.b_full[s], ph, 203);
-            fence_after_sync();
-            const uint32_t b_addr = smem_u32(S.B[s]);
+#pragma unroll 1
+          for (uint32_t o = 0; o < K4_STEPS / K4_STAGES; ++o) {
+            const uint32_t ph = o & 1;            // (step / 6) & 1: steps per jb (60) and per pair are multiples of 12
 #pragma unroll
-            for (int t = 0; t < K4_TILES; ++t) {
+            for (int sg = 0; sg < K4_STAGES; ++sg) {
+              TC_WAIT(&S.a_full[sg], ph, 202);
+              TC_WAIT(&S.b_full[bs], bph, 203);
+              fence_after_sync();
+              if (leader) {
+                const uint32_t b_lo = bd_lo + ((bs * K4_BSLICE) >> 4);
 #pragma unroll
-              for (int kk = 0; kk < 2; ++kk) {
-                const uint64_t bd = make_desc_kmajor_noswizzle(b_addr + kk * 2048, 1024, 128);
-                mma_ts(tmem + t * 64, tmem + K4_ACOL0 + s * K4_STAGE_COLS + t * 16 + kk * 8, bd, idesc,
-                       (st | kk) != 0);
+                for (int t = 0; t < K4_TILES; ++t) {
+#pragma unroll
+                  for (int kk = 0; kk < 2; ++kk) {
+                    const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_lo + ((kk * 2048) >> 4));
+                    mma_ts(tmem + t * 64, tmem + K4_ACOL0 + sg * K4_STAGE_COLS + t * 16 + kk * 8, bd, idesc,
+                           (o | (uint32_t)sg | (uint32_t)kk) != 0);
+                  }
+                }
+                commit(&S.a_empty[sg]);
+                commit(&S.b_empty[bs]);
               }
+              __syncwarp();
+              if (++bs == K4_BSLOTS) { bs = 0; bph ^= 1; }
             }
-            commit(&S.empty[s]);
           }
-          commit(&S.d_full);
+          if (leader) commit(&S.d_full);
+          __syncwarp();
         }
       }
     }
@@ -189,89 +223,104 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
           const int i = t * 128 + q * 32 + lane;
           const int ib = i / S15, di = i - ib * S15;
           const int64_t m = (int64_t)p * PAIR_ROWS + ib * NB + jb;
+          uint32_t v[4][16];
 #pragma unroll
-          for (int c0 = 0; c0 < 64; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * 64 + c0, v);
-            tmem_ld_wait();
-            if (i < WF) {
+          for (int c = 0; c < 4; ++c) tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * 64 + c * 16, v[c]);
+          tmem_ld_wait();
+          if (t == K4_TILES - 1) {             // everything is in registers: hand D back before the stores
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.d_empty);
+          }
+          if (i < WF) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
 #pragma unroll
               for (int h8 = 0; h8 < 2; ++h8) {
                 uint32_t pk[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const int o = c0 + h8 * 8 + 2 * j;
-                  __half2 hh = __floats2half2_rn(__uint_as_float(v[h8 * 8 + 2 * j]) + S.bias[o],
-                                                 __uint_as_float(v[h8 * 8 + 2 * j + 1]) + S.bias[o + 1]);
+                  const int o = c * 16 + h8 * 8 + 2 * j;
+                  __half2 hh = __floats2half2_rn(__uint_as_float(v[c][h8 * 8 + 2 * j]) + S.bias[o],
+                                                 __uint_as_float(v[c][h8 * 8 + 2 * j + 1]) + S.bias[o + 1]);
                   pk[j] = *reinterpret_cast<uint32_t*>(&hh);
                 }
-                const int k8 = di * 8 + (c0 >> 3) + h8;           // plane = (di, o/8)
+                const int k8 = di * 8 + c * 2 + h8;               // plane = (di, o/8)
                 *reinterpret_cast<uint4*>(o1 + ((size_t)k8 * rows_pad + m) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
             }
           }
         }
-        fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S.d_empty);
       }
     }
   } else if (warp >= 8) {
     // ===================== producers: |l - r| -> TMEM ==========================================
-    const int pw = warp - 8, q = pw & 3, half = pw >> 2;
+    // 8 warps: TMEM lane quarter q, K half `half` (16 of the 32 channels of a step).  A thread owns
+    // LEFT rows q*32+lane (+128, +256); their 16 channels of the current chunk live in registers
+    // (prefetched from L2 one (jb, chunk) ahead), the RIGHT row comes by broadcast LDS.128.
+    const int pw = warp - 8, q = pw & 3, half = (pw >> 2) & 1;
     const int row0 = q * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + K4_ACOL0 + half * 8;
+    uint32_t pi = 0, sg = 0, ph = 0;
     if (!r_per_pair) { TC_WAIT(&S.r_full, 0, 401); }
-    uint32_t it = 0, pi = 0;
     for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++pi) {
-      TC_WAIT(&S.l_full, pi & 1, 402);
-      for (int jb = 0; jb < NB; ++jb) {
+      if (r_per_pair) { TC_WAIT(&S.r_full, pi & 1, 402); }
+      const __half* Lp = L16 + (size_t)p * WF * K4_PITCH;
+      uint32_t Ln[K4_TILES][8];               // next chunk's LEFT registers (prefetch)
+      auto fetch = [&](int cc) {
+#pragma unroll
+        for (int t = 0; t < K4_TILES; ++t) {
+          const int i = t * 128 + row0;
+          uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+          if (i < WF) {
+            const uint4* src = reinterpret_cast<const uint4*>(Lp + (size_t)i * K4_PITCH + cc * 32 + half * 16);
+            a = __ldg(src);
+            b = __ldg(src + 1);
+          }
+          Ln[t][0] = a.x; Ln[t][1] = a.y; Ln[t][2] = a.z; Ln[t][3] = a.w;
+          Ln[t][4] = b.x; Ln[t][5] = b.y; Ln[t][6] = b.z; Ln[t][7] = b.w;
+        }
+      };
+      fetch(0);
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          const int ch = cc * 32 + half * 16;
-          __half2 Lr[K4_TILES][8];
+      for (int u = 0; u < NB * 4; ++u) {       // u = jb*4 + cc
+        const int jb = u >> 2, cc = u & 3;
+        uint32_t Lr[K4_TILES][8];
+#pragma unroll
+        for (int t = 0; t < K4_TILES; ++t)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) Lr[t][j] = Ln[t][j];
+        fetch((cc + 1) & 3);                   // the chunk sequence repeats for every jb
+        const int ch = cc * 32 + half * 16;
+#pragma unroll 1
+        for (int dj = 0; dj < S15; ++dj) {
+          const __half* rrow = &S.R[(jb * S15 + dj) * K4_PITCH + ch];
+          const uint4 ra = *reinterpret_cast<const uint4*>(rrow);                  // broadcast LDS
+          const uint4 rb = *reinterpret_cast<const uint4*>(rrow + 8);
+          const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+          TC_WAIT(&S.a_empty[sg], ph ^ 1, 403);
+          fence_after_sync();
 #pragma unroll
           for (int t = 0; t < K4_TILES; ++t) {
-            const int i = t * 128 + row0;
-            if (i < WF) {
-              const uint4 a = *reinterpret_cast<const uint4*>(&S.L[i * CF + ch]);
-              const uint4 b = *reinterpret_cast<const uint4*>(&S.L[i * CF + ch + 8]);
-              const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            uint32_t o[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) Lr[t][j] = *reinterpret_cast<const __half2*>(&w[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) Lr[t][j] = __float2half2_rn(0.f);
+            for (int j = 0; j < 8; ++j) {
+              // |l - r|: subtract on the FMA pipe, clear both sign bits on the ALU pipe (LOP3)
+              const __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&Lr[t][j]),
+                                        *reinterpret_cast<const __half2*>(&rw[j]));
+              o[j] = *reinterpret_cast<const uint32_t*>(&d) & 0x7fff7fffu;
             }
+            tmem_st_x8(lane_addr + sg * K4_STAGE_COLS + t * 16, o);
           }
-#pragma unroll 1
-          for (int dj = 0; dj < S15; ++dj, ++it) {
-            const uint32_t s = it % K4_STAGES, ph = (it / K4_STAGES) & 1;
-            const int rrow = jb * S15 + dj;
-            const uint4 ra = *reinterpret_cast<const uint4*>(&S.R[rrow * CF + ch]);        // broadcast
-            const uint4 rb = *reinterpret_cast<const uint4*>(&S.R[rrow * CF + ch + 8]);
-            const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-            TC_WAIT(&S.empty[s], ph ^ 1, 403);
-            fence_after_sync();
-#pragma unroll
-            for (int t = 0; t < K4_TILES; ++t) {
-              uint32_t o[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                // |l - r|: subtract on the FMA pipe, clear both sign bits on the ALU pipe (LOP3)
-                const __half2 d = __hsub2(Lr[t][j], *reinterpret_cast<const __half2*>(&rw[j]));
-                o[j] = *reinterpret_cast<const uint32_t*>(&d) & 0x7fff7fffu;
-              }
-              tmem_st_x8(tmem + ((uint32_t)(q * 32) << 16) + K4_ACOL0 + s * K4_STAGE_COLS + t * 16 + half * 8, o);
-            }
-            tmem_st_wait();
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.a_full[s]);
-          }
+          tmem_st_wait();
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S.a_full[sg]);
+          if (++sg == K4_STAGES) { sg = 0; ph ^= 1; }
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&S.l_empty);
+      if (r_per_pair && lane == 0) mbar_arrive(&S.r_empty);
     }
   }
 done:
@@ -287,46 +336,59 @@ constexpr int G_THREADS = 256;
 constexpr int G_STAGES = 4;
 constexpr int G_ROWS = 512;                      // 4 row tiles of 128
 constexpr int G_A_BYTES = 4 * G_ROWS * 16;       // 4 planes x 512 rows x 16 B = 32 KB
-constexpr int G_B_BYTES = 4 * 128 * 16;          // 4 planes x 128 n x 16 B   =  8 KB
+constexpr int G_B_BYTES_MAX = 4 * 128 * 16;      // 4 planes x N (<=128) x 16 B
 
 struct GSmem {
   uint8_t A[G_STAGES][G_A_BYTES];
-  uint8_t B[G_STAGES][G_B_BYTES];
+  uint8_t B[G_STAGES][G_B_BYTES_MAX];
   float bias[128];
   uint64_t full[G_STAGES], empty[G_STAGES], d_full;
   uint32_t tmem_base;
 };
 
+// One "run" = a 1-D sequence of rows (pixels) whose channels live in C8-interleaved planes
+// [plane][row][8] with `a_pitch` rows per plane.  blockIdx.x = 512-row tile inside the run,
+// blockIdx.y = run (image row for the 2-D leg layers), blockIdx.z = 128-wide N slice.
+// K loop = slabs of four (plane, row shift) copies: the row shift is the convolution tap along
+// the run (implicit im2col at the copy level), the plane picks (input row tap, channel chunk).
 struct GemmArgs {
-  const __half* A;            // planes [n_planes][rows_pad][8]
-  int64_t rows_pad;
-  const int* slab_plane;      // first of the 4 consecutive planes of each slab
-  const int* slab_shift;      // row shift of each slab (implicit im2col)
+  const __half* A;
+  int64_t a_pitch;            // rows per input plane
+  const int* copy_plane;      // [n_slabs*4] plane of each copy, relative to the run's first plane
+  const int* copy_shift;      // [n_slabs*4] row shift of each copy
   int n_slabs;
-  const __half* Bp;           // [n_half][n_slabs][4][128][8]
-  const float* bias;          // [n_half*128]
-  int64_t M;                  // valid rows
-  // epilogue 1: relu -> fp16 planes
-  __half* out_planes; int64_t out_rows_pad;
-  // epilogue 2: relu -> dot with the Dense kernel -> per-row partial sums
+  const __half* Bp;           // [gridDim.z][n_slabs][4][NT][8]
+  const float* bias;          // [gridDim.z * NT]
+  int64_t M;                  // valid rows per run
+  int runs_per_img;           // blockIdx.y = img * runs_per_img + run
+  int in_img_planes;          // planes per input image
+  int in_run_planes;          // plane advance per run (stride_h * C8_in)
+  // epilogue 1: bias + ReLU -> fp16 planes [y * out_run_planes + n/8][row][8]
+  __half* out_planes; int64_t out_pitch; int out_run_planes;
+  // epilogue 2: bias + ReLU -> dot with the Dense kernel -> per-row partial sums
   const float* wd; float* partial; int grid_w, valid_w, valid_h, n_total;
+  // epilogue 3: bias + ReLU -> fp32 row-major [y][row][NT]
+  float* out_f32;
+  int n_valid;                // output channels actually present (<= NT); 0 = NT
 };
 
-template <int EPI>
+template <int EPI, int NT>
 __global__ void __launch_bounds__(G_THREADS, 1)
 k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   GSmem& S = *reinterpret_cast<GSmem*>(smem_raw);
+  constexpr int B_BYTES = 4 * NT * 16;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t row0 = (int64_t)blockIdx.x * G_ROWS;
-  const int nh = blockIdx.y;
+  const int y = blockIdx.y, nh = blockIdx.z;
+  const int64_t in_base = (int64_t)(y / g.runs_per_img) * g.in_img_planes + (int64_t)(y % g.runs_per_img) * g.in_run_planes;
 
   if (tid == 0) {
     for (int s = 0; s < G_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
     mbar_init(&S.d_full, 1);
     mbar_fence_init();
   }
-  if (tid < 128) S.bias[tid] = g.bias[nh * 128 + tid];
+  if (tid < NT) S.bias[tid] = g.bias[nh * NT + tid];
   if (warp == 2) tmem_alloc(&S.tmem_base, 512);
   fence_before_sync();
   __syncthreads();
@@ -335,39 +397,50 @@ k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
 
   if (warp == 0) {
     if (lane == 0) {
+      uint32_t s = 0, ph = 0;
       for (int sl = 0; sl < g.n_slabs; ++sl) {
-        const uint32_t s = sl % G_STAGES, ph = (sl / G_STAGES) & 1;
         TC_WAIT(&S.empty[s], ph ^ 1, 501);
-        mbar_arrive_expect_tx(&S.full[s], G_A_BYTES + G_B_BYTES);
-        const int plane = g.slab_plane[sl];
-        const int64_t r = row0 + g.slab_shift[sl];
+        mbar_arrive_expect_tx(&S.full[s], G_A_BYTES + B_BYTES);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          bulk_g2s(S.A[s] + j * (G_ROWS * 16), g.A + ((size_t)(plane + j) * g.rows_pad + r) * 8, G_ROWS * 16, &S.full[s]);
-        bulk_g2s(S.B[s], g.Bp + ((size_t)nh * g.n_slabs + sl) * (G_B_BYTES / 2), G_B_BYTES, &S.full[s]);
+        for (int j = 0; j < 4; ++j) {
+          const int64_t plane = in_base + g.copy_plane[sl * 4 + j];
+          const int64_t r = row0 + g.copy_shift[sl * 4 + j];
+          bulk_g2s(S.A[s] + j * (G_ROWS * 16), g.A + ((size_t)plane * g.a_pitch + r) * 8, G_ROWS * 16, &S.full[s]);
+        }
+        bulk_g2s(S.B[s], g.Bp + ((size_t)nh * g.n_slabs + sl) * (B_BYTES / 2), B_BYTES, &S.full[s]);
+        if (++s == G_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(128, 128);
-      for (int sl = 0; sl < g.n_slabs; ++sl) {
-        const uint32_t s = sl % G_STAGES, ph = (sl / G_STAGES) & 1;
-        TC_WAIT(&S.full[s], ph, 502);
-        fence_after_sync();
-        const uint32_t a_addr = smem_u32(S.A[s]), b_addr = smem_u32(S.B[s]);
+    // warp-uniform loop, one elected lane issues; descriptors advance by 32-bit adds
+    const uint32_t idesc = make_idesc_f16(128, NT);
+    const bool leader = elect_one() != 0;
+    const uint64_t ad0 = make_desc_kmajor_noswizzle(smem_u32(S.A[0]), G_ROWS * 16, 128);
+    const uint64_t bd0 = make_desc_kmajor_noswizzle(smem_u32(S.B[0]), NT * 16, 128);
+    const uint32_t ad_hi = (uint32_t)(ad0 >> 32), ad_lo = (uint32_t)ad0;
+    const uint32_t bd_hi = (uint32_t)(bd0 >> 32), bd_lo = (uint32_t)bd0;
+    uint32_t sg = 0, ph = 0;
+    for (int sl = 0; sl < g.n_slabs; ++sl) {
+      TC_WAIT(&S.full[sg], ph, 502);
+      fence_after_sync();
+      if (leader) {
+        const uint32_t a_off = (sg * G_A_BYTES) >> 4, b_off = (sg * G_B_BYTES_MAX) >> 4;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
-            const uint64_t ad = make_desc_kmajor_noswizzle(a_addr + t * 128 * 16 + kk * 2 * (G_ROWS * 16), G_ROWS * 16, 128);
-            const uint64_t bd = make_desc_kmajor_noswizzle(b_addr + kk * 2 * (128 * 16), 128 * 16, 128);
-            mma_ss(tmem + t * 128, ad, bd, idesc, (sl | kk) != 0);
+            const uint64_t ad = ((uint64_t)ad_hi << 32) | (uint64_t)(ad_lo + a_off + ((t * 128 * 16 + kk * 2 * (G_ROWS * 16)) >> 4));
+            const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(bd_lo + b_off + ((kk * 2 * (NT * 16)) >> 4));
+            mma_ss(tmem + t * NT, ad, bd, idesc, (sl | kk) != 0);
           }
         }
-        commit(&S.empty[s]);
+        commit(&S.empty[sg]);
       }
-      commit(&S.d_full);
+      __syncwarp();
+      if (++sg == G_STAGES) { sg = 0; ph ^= 1; }
     }
+    if (leader) commit(&S.d_full);
+    __syncwarp();
   } else if (warp >= 4) {
     const int q = warp & 3;
     TC_WAIT(&S.d_full, 0, 503);
@@ -375,26 +448,63 @@ k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
 #pragma unroll 1
     for (int t = 0; t < 4; ++t) {
       const int64_t r = row0 + t * 128 + q * 32 + lane;
-      if (EPI == 1) {
+      if (EPI == 1 || EPI == 3 || EPI == 4) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 16) {
+        for (int c0 = 0; c0 < NT; c0 += 16) {
           uint32_t v[16];
-          tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * 128 + c0, v);
+          tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * NT + c0, v);
           tmem_ld_wait();
-          if (r < g.M) {
+          if (r < g.M && (g.n_valid == 0 || c0 < g.n_valid)) {
+            if (EPI == 4) {
+              // bias + ReLU -> hi/lo fp16 split planes (x = hi + lo to 2^-22): the next layer's
+              // three-term product keeps the leg at fp32-grade accuracy on the fp16 tensor pipe
 #pragma unroll
-            for (int h8 = 0; h8 < 2; ++h8) {
-              uint32_t pk[4];
+              for (int h8 = 0; h8 < 2; ++h8) {
+                uint32_t ph[4], pl[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int n = c0 + h8 * 8 + 2 * j;
-                __half2 hh = __floats2half2_rn(fmaxf(__uint_as_float(v[h8 * 8 + 2 * j]) + S.bias[n], 0.f),
-                                               fmaxf(__uint_as_float(v[h8 * 8 + 2 * j + 1]) + S.bias[n + 1], 0.f));
-                pk[j] = *reinterpret_cast<uint32_t*>(&hh);
+                for (int j = 0; j < 4; ++j) {
+                  const int n = c0 + h8 * 8 + 2 * j;
+                  const float a = fmaxf(__uint_as_float(v[h8 * 8 + 2 * j]) + S.bias[n], 0.f);
+                  const float b = fmaxf(__uint_as_float(v[h8 * 8 + 2 * j + 1]) + S.bias[n + 1], 0.f);
+                  const __half2 hi = __floats2half2_rn(a, b);
+                  const float2 hf = __half22float2(hi);
+                  const __half2 lo = __floats2half2_rn(a - hf.x, b - hf.y);
+                  ph[j] = *reinterpret_cast<const uint32_t*>(&hi);
+                  pl[j] = *reinterpret_cast<const uint32_t*>(&lo);
+                }
+                const int c8 = (c0 >> 3) + h8;
+                const int64_t plane = (int64_t)y * g.out_run_planes + c8;
+                *reinterpret_cast<uint4*>(g.out_planes + ((size_t)plane * g.out_pitch + r) * 8) =
+                    make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                *reinterpret_cast<uint4*>(g.out_planes + ((size_t)(plane + g.out_run_planes / 2) * g.out_pitch + r) * 8) =
+                    make_uint4(pl[0], pl[1], pl[2], pl[3]);
               }
-              const int plane = nh * 16 + (c0 >> 3) + h8;
-              *reinterpret_cast<uint4*>(g.out_planes + ((size_t)plane * g.out_rows_pad + r) * 8) =
-                  make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            } else if (EPI == 1) {
+#pragma unroll
+              for (int h8 = 0; h8 < 2; ++h8) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int n = c0 + h8 * 8 + 2 * j;
+                  __half2 hh = __floats2half2_rn(fmaxf(__uint_as_float(v[h8 * 8 + 2 * j]) + S.bias[n], 0.f),
+                                                 fmaxf(__uint_as_float(v[h8 * 8 + 2 * j + 1]) + S.bias[n + 1], 0.f));
+                  pk[j] = *reinterpret_cast<uint32_t*>(&hh);
+                }
+                const int64_t plane = (int64_t)y * g.out_run_planes + nh * (NT / 8) + (c0 >> 3) + h8;
+                *reinterpret_cast<uint4*>(g.out_planes + ((size_t)plane * g.out_pitch + r) * 8) =
+                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            } else {
+              float* dst = g.out_f32 + ((size_t)y * g.M + r) * NT + c0;
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                float4 o;
+                o.x = fmaxf(__uint_as_float(v[j4 * 4 + 0]) + S.bias[c0 + j4 * 4 + 0], 0.f);
+                o.y = fmaxf(__uint_as_float(v[j4 * 4 + 1]) + S.bias[c0 + j4 * 4 + 1], 0.f);
+                o.z = fmaxf(__uint_as_float(v[j4 * 4 + 2]) + S.bias[c0 + j4 * 4 + 2], 0.f);
+                o.w = fmaxf(__uint_as_float(v[j4 * 4 + 3]) + S.bias[c0 + j4 * 4 + 3], 0.f);
+                reinterpret_cast<float4*>(dst)[j4] = o;
+              }
             }
           }
         }
@@ -402,14 +512,14 @@ k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
         // row r = pair * (grid_w*grid_w) + y * grid_w + x ; valid output pixel iff y < valid_h, x < valid_w
         const int per = g.grid_w * g.grid_w;
         const int rem = (int)(r % per);
-        const int y = rem / g.grid_w, x = rem - y * g.grid_w;
-        const bool valid = (r < g.M) && (y < g.valid_h) && (x < g.valid_w);
-        const float* wrow = g.wd + ((size_t)(valid ? (y * g.valid_w + x) : 0) * g.n_total + nh * 128);
+        const int yy = rem / g.grid_w, xx = rem - yy * g.grid_w;
+        const bool valid = (r < g.M) && (yy < g.valid_h) && (xx < g.valid_w);
+        const float* wrow = g.wd + ((size_t)(valid ? (yy * g.valid_w + xx) : 0) * g.n_total + nh * NT);
         float acc = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 16) {
+        for (int c0 = 0; c0 < NT; c0 += 16) {
           uint32_t v[16];
-          tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * 128 + c0, v);
+          tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * NT + c0, v);
           tmem_ld_wait();
           if (valid) {
 #pragma unroll
@@ -430,6 +540,282 @@ done:
   fence_before_sync();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Correlation (yaw) head on tensor cores.
+//   G = L R^T (360 x 360, K = 128), corr[k] = sum_j G[(k + j + 180) mod 360, j]
+//   (RangePadding2D.py:34 + NormalizedCorrelation2D.py:96-109), yaw = 180 - argmax (infer.py:158).
+// fp16 alone (10-bit mantissa) is not enough to keep the argmax of a flat correlation curve, so the
+// operands are split hi/lo (x = hi + lo exactly to 2^-22) and G = Lhi Rhi + Llo Rhi + Lhi Rlo is
+// accumulated in fp32 in TMEM: three tcgen05.mma per K16 step, fp32-grade result, still < 5 % of
+// c_conv1's tensor time.  One CTA owns one half of R's rows (N = 192, zero-padded past 360) for all
+// of its pairs; L arrives as 32 KB stages (row tile x K half, hi+lo) through a 3-deep bulk-copy
+// ring.  The diagonal sums never touch memory: each epilogue warp reads its 32 rows of a finished
+// 128 x 192 tile from TMEM and rotates a running accumulator across lanes (bin(lane, col+1) ==
+// bin(lane-1, col)), flushing one finished bin per column.
+// ------------------------------------------------------------------------------------------------
+constexpr int C6_THREADS = 256;
+constexpr int C6_STAGES = 3;
+constexpr int C6_STAGE_BYTES = 32768;            // [hi,lo][8 planes][128 rows][8] fp16
+constexpr int C6_R_BYTES = 98304;                // [hi,lo][16 planes][192 rows][8] fp16
+constexpr int C6_VOL_L_BYTES = 6 * C6_STAGE_BYTES;
+constexpr int C6_VOL_R_BYTES = 2 * C6_R_BYTES;
+
+struct C6Smem {
+  uint8_t R[C6_R_BYTES];
+  uint8_t A[C6_STAGES][C6_STAGE_BYTES];
+  float corr[4][WF];
+  uint64_t full[C6_STAGES], empty[C6_STAGES], d_full[2], d_empty[2], r_full, r_empty, epi;
+  uint32_t tmem_base;
+};
+
+// fp32 volumes -> hi/lo fp16 split in the stage layout of k_corr_tc (zero rows past 360)
+__global__ void __launch_bounds__(256)
+k_pack_corr_L(const float* __restrict__ bank, const int32_t* __restrict__ idx, int n, __half* __restrict__ out) {
+  // one thread per (pair, tile, khalf, plane j, row): 8 channels
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = 3 * 2 * 8 * 128;
+  if (i >= (int64_t)n * per) return;
+  const int p = (int)(i / per);
+  int r = (int)(i % per);
+  const int row = r % 128; r /= 128;
+  const int j = r % 8; r /= 8;
+  const int kh = r % 2; r /= 2;
+  const int t = r;
+  const int vrow = t * 128 + row;
+  const int c = kh * 64 + j * 8;
+  float v[8];
+  if (vrow < WF) {
+    const int64_t src = (idx ? idx[p] : p);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(bank + (src * WF + vrow) * CF + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bank + (src * WF + vrow) * CF + c + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  }
+  __half hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    hi[e] = __float2half_rn(v[e]);
+    lo[e] = __float2half_rn(v[e] - __half2float(hi[e]));
+  }
+  __half* base = out + (size_t)p * (C6_VOL_L_BYTES / 2) + (size_t)(t * 2 + kh) * (C6_STAGE_BYTES / 2);
+  *reinterpret_cast<uint4*>(base + ((size_t)j * 128 + row) * 8) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(base + (C6_STAGE_BYTES / 4) + ((size_t)j * 128 + row) * 8) = *reinterpret_cast<const uint4*>(lo);
+}
+
+__global__ void __launch_bounds__(256)
+k_pack_corr_R(const float* __restrict__ bank, const int32_t* __restrict__ idx, int n, __half* __restrict__ out) {
+  // one thread per (pair, nhalf, plane, row): 8 channels
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = 2 * 16 * 192;
+  if (i >= (int64_t)n * per) return;
+  const int p = (int)(i / per);
+  int r = (int)(i % per);
+  const int row = r % 192; r /= 192;
+  const int pl = r % 16; r /= 16;
+  const int h = r;
+  const int vrow = h * 192 + row;
+  float v[8];
+  if (vrow < WF) {
+    const int64_t src = (idx ? idx[p] : p);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(bank + (src * WF + vrow) * CF + pl * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bank + (src * WF + vrow) * CF + pl * 8 + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  }
+  __half hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    hi[e] = __float2half_rn(v[e]);
+    lo[e] = __float2half_rn(v[e] - __half2float(hi[e]));
+  }
+  __half* base = out + (size_t)p * (C6_VOL_R_BYTES / 2) + (size_t)h * (C6_R_BYTES / 2);
+  *reinterpret_cast<uint4*>(base + ((size_t)pl * 192 + row) * 8) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(base + (C6_R_BYTES / 4) + ((size_t)pl * 192 + row) * 8) = *reinterpret_cast<const uint4*>(lo);
+}
+
+__device__ __forceinline__ int wrap360(int x) {
+  x %= WF;
+  return x < 0 ? x + WF : x;
+}
+
+__global__ void __launch_bounds__(C6_THREADS, 1)
+k_corr_tc(const __half* __restrict__ Lc, const __half* __restrict__ Rc, int r_per_pair, int n_pairs,
+          float* __restrict__ corr_part, int* __restrict__ err) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  C6Smem& S = *reinterpret_cast<C6Smem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x & 1;
+  const int cta = blockIdx.x >> 1, n_cta = gridDim.x >> 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < C6_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&S.d_full[b], 1); mbar_init(&S.d_empty[b], 4); }
+    mbar_init(&S.r_full, 1); mbar_init(&S.r_empty, 1); mbar_init(&S.epi, 4);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(&S.tmem_base, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (!r_per_pair) {
+        mbar_arrive_expect_tx(&S.r_full, C6_R_BYTES);
+        bulk_g2s(S.R, reinterpret_cast<const uint8_t*>(Rc) + (size_t)h * C6_R_BYTES, C6_R_BYTES, &S.r_full);
+      }
+      uint32_t it = 0, pi = 0;
+      for (int p = cta; p < n_pairs; p += n_cta, ++pi) {
+        if (r_per_pair) {
+          TC_WAIT(&S.r_empty, (pi & 1) ^ 1, 601);
+          mbar_arrive_expect_tx(&S.r_full, C6_R_BYTES);
+          bulk_g2s(S.R, reinterpret_cast<const uint8_t*>(Rc) + (size_t)p * C6_VOL_R_BYTES + (size_t)h * C6_R_BYTES,
+                   C6_R_BYTES, &S.r_full);
+        }
+        for (int st = 0; st < 6; ++st, ++it) {
+          const uint32_t s = it % C6_STAGES, ph = (it / C6_STAGES) & 1;
+          TC_WAIT(&S.empty[s], ph ^ 1, 602);
+          mbar_arrive_expect_tx(&S.full[s], C6_STAGE_BYTES);
+          bulk_g2s(S.A[s], reinterpret_cast<const uint8_t*>(Lc) + (size_t)p * C6_VOL_L_BYTES + (size_t)st * C6_STAGE_BYTES,
+                   C6_STAGE_BYTES, &S.full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    {
+      const uint32_t idesc = make_idesc_f16(128, 192);
+      const bool leader = elect_one() != 0;
+      const uint64_t ad0 = make_desc_kmajor_noswizzle(smem_u32(S.A[0]), 2048, 128);
+      const uint64_t bd0 = make_desc_kmajor_noswizzle(smem_u32(S.R), 3072, 128);
+      const uint32_t ad_hi = (uint32_t)(ad0 >> 32), ad_lo = (uint32_t)ad0;
+      const uint32_t bd_hi = (uint32_t)(bd0 >> 32), bd_lo = (uint32_t)bd0;
+      uint32_t sg = 0, ph = 0, tileit = 0, pi = 0;
+      if (!r_per_pair) { TC_WAIT(&S.r_full, 0, 603); }
+      for (int p = cta; p < n_pairs; p += n_cta, ++pi) {
+        if (r_per_pair) { TC_WAIT(&S.r_full, pi & 1, 604); }
+        for (int t = 0; t < 3; ++t, ++tileit) {
+          const uint32_t buf = tileit & 1;
+          TC_WAIT(&S.d_empty[buf], ((tileit >> 1) & 1) ^ 1, 605);
+          fence_after_sync();
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
+            TC_WAIT(&S.full[sg], ph, 606);
+            fence_after_sync();
+            if (leader) {
+              const uint32_t a_off = (sg * C6_STAGE_BYTES) >> 4;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t a_hi = ((uint64_t)ad_hi << 32) | (uint64_t)(ad_lo + a_off + ((kk * 2 * 2048) >> 4));
+                const uint64_t a_lo = ((uint64_t)ad_hi << 32) | (uint64_t)(ad_lo + a_off + ((16384 + kk * 2 * 2048) >> 4));
+                const uint64_t b_hi = ((uint64_t)bd_hi << 32) | (uint64_t)(bd_lo + (((kh * 8 + kk * 2) * 3072) >> 4));
+                const uint64_t b_lo = ((uint64_t)bd_hi << 32) | (uint64_t)(bd_lo + ((49152 + (kh * 8 + kk * 2) * 3072) >> 4));
+                mma_ss(tmem + buf * 192, a_hi, b_hi, idesc, (kh | kk) != 0);
+                mma_ss(tmem + buf * 192, a_lo, b_hi, idesc, 1);
+                mma_ss(tmem + buf * 192, a_hi, b_lo, idesc, 1);
+              }
+              commit(&S.empty[sg]);
+            }
+            __syncwarp();
+            if (++sg == C6_STAGES) { sg = 0; ph ^= 1; }
+          }
+          if (leader) commit(&S.d_full[buf]);
+          __syncwarp();
+        }
+        if (r_per_pair && leader) commit(&S.r_empty);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    float* my = S.corr[q];
+    uint32_t tileit = 0, rz = 0;      // rz: rendezvous count of the 4 epilogue warps (bounded mbarrier, never bar.sync)
+    for (int p = cta; p < n_pairs; p += n_cta) {
+      for (int k = lane; k < WF; k += 32) my[k] = 0.f;
+      __syncwarp();
+      for (int t = 0; t < 3; ++t, ++tileit) {
+        const uint32_t buf = tileit & 1;
+        TC_WAIT(&S.d_full[buf], (tileit >> 1) & 1, 607);
+        fence_after_sync();
+        // bin(lane, col) = (i - j - 180) mod 360 with i = t*128 + q*32 + lane, j = h*192 + col
+        const int b31 = t * 128 + q * 32 + 31 - h * 192 - 180;     // bin of lane 31 at col 0 (before wrap)
+        float acc = 0.f, pend = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < 6; ++ch) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + buf * 192 + ch * 32, v);
+          tmem_ld_wait();
+          if (ch == 5) {                     // all of this tile is in registers / consumed: release the buffer
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.d_empty[buf]);
+          }
+#pragma unroll
+          for (int cc = 0; cc < 32; ++cc) {
+            if (ch > 0 || cc > 0) {
+              // retire lane 31's accumulator (the bin that leaves this warp) into lane (col-1)&31's pend
+              const float out = __shfl_sync(0xffffffffu, acc, 31);
+              if (lane == ((cc + 31) & 31)) pend = out;
+              if (cc == 0) {
+                // cols (ch-1)*32 .. ch*32-1 retired: lane l holds the bin of lane 31 at col (ch-1)*32 + l
+                const int bin = wrap360(b31 - ((ch - 1) * 32 + lane));
+                my[bin] += pend;
+                __syncwarp();
+              }
+              acc = __shfl_up_sync(0xffffffffu, acc, 1);
+              if (lane == 0) acc = 0.f;
+            }
+            acc += __uint_as_float(v[cc]);
+          }
+        }
+        // tail: cols 160..190 retired into lanes 0..30 of pend; col 191's accumulators still in acc
+        if (lane < 31) my[wrap360(b31 - (160 + lane))] += pend;
+        __syncwarp();
+        my[wrap360(b31 - 31 + lane - 191)] += acc;
+        __syncwarp();
+      }
+      // combine the four warps' private arrays in a fixed order (bit-reproducible)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.epi);
+      TC_WAIT(&S.epi, rz & 1, 608);
+      ++rz;
+      for (int k = tid - 128; k < WF; k += 128)
+        corr_part[((size_t)p * 2 + h) * WF + k] = ((S.corr[0][k] + S.corr[1][k]) + S.corr[2][k]) + S.corr[3][k];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.epi);
+      TC_WAIT(&S.epi, rz & 1, 609);
+      ++rz;
+    }
+  }
+done:
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+__global__ void __launch_bounds__(384)
+k_corr_finalize(const float* __restrict__ part, float* __restrict__ corr_out, int32_t* __restrict__ yaw) {
+  __shared__ float s_corr[WF];
+  const int p = blockIdx.x;
+  for (int k = threadIdx.x; k < WF; k += blockDim.x) {
+    const float c = part[((size_t)p * 2) * WF + k] + part[((size_t)p * 2 + 1) * WF + k];
+    s_corr[k] = c;
+    if (corr_out) corr_out[(size_t)p * WF + k] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int best = 0;
+    float bv = s_corr[0];
+    for (int k = 1; k < WF; ++k)
+      if (s_corr[k] > bv) { bv = s_corr[k]; best = k; }
+    yaw[p] = WF / 2 - best;
+  }
 }
 
 // Dense bias + sigmoid: fixed-order reduction of the per-row partial sums of one pair
@@ -461,8 +847,15 @@ void tc_free(ovn_handle* h) {
   TcState* t = h->tc;
   if (!t) return;
   void* bufs[] = {t->w1p, t->w2p, t->w3p, t->slab2_plane, t->slab2_shift, t->slab3_plane, t->slab3_shift,
-                  t->l16, t->r16, t->o1, t->x3, t->partial, t->d_err};
+                  t->l16, t->r16, t->o1, t->x3, t->partial, t->d_err, t->lc, t->rc, t->corr_part};
   for (void* b : bufs) if (b) cudaFree(b);
+  for (int l = 0; l < kMaxLegLayers; ++l) {
+    if (t->wleg[l]) cudaFree(t->wleg[l]);
+    if (t->leg_plane[l]) cudaFree(t->leg_plane[l]);
+    if (t->leg_shift[l]) cudaFree(t->leg_shift[l]);
+  }
+  if (t->actp[0]) cudaFree(t->actp[0]);
+  if (t->actp[1]) cudaFree(t->actp[1]);
   delete t;
   h->tc = nullptr;
 }
@@ -496,10 +889,10 @@ int tc_pack_weights(ovn_handle* h) {
           }
   // c_conv2: K index k = di*64 + o, plane k8 = di*8 + o/8; slab = 4 planes; B[sl][j][n][e] = W2[di][o][n]
   std::vector<__half> p2((size_t)30 * 4 * 128 * 8);
-  std::vector<int> s2p(30), s2s(30, 0);
+  std::vector<int> s2p(30 * 4), s2s(30 * 4, 0);
   for (int sl = 0; sl < 30; ++sl) {
-    s2p[sl] = sl * 4;
     for (int j = 0; j < 4; ++j) {
+      s2p[sl * 4 + j] = sl * 4 + j;
       const int k8 = sl * 4 + j, di = k8 / 8, o8 = k8 % 8;
       for (int n = 0; n < 128; ++n)
         for (int e = 0; e < 8; ++e)
@@ -508,13 +901,12 @@ int tc_pack_weights(ovn_handle* h) {
   }
   // c_conv3: slab = (dy, dx, channel group g of 32); planes c8 = g*4..g*4+3 of X3; shift = dy*24 + dx
   std::vector<__half> p3((size_t)2 * 36 * 4 * 128 * 8);
-  std::vector<int> s3p(36), s3s(36);
+  std::vector<int> s3p(36 * 4), s3s(36 * 4);
   for (int dy = 0; dy < 3; ++dy)
     for (int dx = 0; dx < 3; ++dx)
       for (int gq = 0; gq < 4; ++gq) {
         const int sl = (dy * 3 + dx) * 4 + gq;
-        s3p[sl] = gq * 4;
-        s3s[sl] = dy * NB + dx;
+        for (int j = 0; j < 4; ++j) { s3p[sl * 4 + j] = gq * 4 + j; s3s[sl * 4 + j] = dy * NB + dx; }
         for (int nh = 0; nh < 2; ++nh)
           for (int j = 0; j < 4; ++j)
             for (int n = 0; n < 128; ++n)
@@ -532,27 +924,140 @@ int tc_pack_weights(ovn_handle* h) {
   if ((rc = upload_vec(h, &t->slab2_shift, s2s)) != OVN_OK) return rc;
   if ((rc = upload_vec(h, &t->slab3_plane, s3p)) != OVN_OK) return rc;
   if ((rc = upload_vec(h, &t->slab3_shift, s3s)) != OVN_OK) return rc;
+  // ---- leg layers 2.. : copy e = (dh, dw, c8) -> plane dh*C8in + c8 of the run, row shift dw
+  size_t max_planes_bytes = 0;
+  for (int l = 0; l < h->n_leg; ++l) {
+    const ConvSpec& L = h->leg[l];
+    const size_t out_bytes = (size_t)L.h_out * 2 * (L.cout / 8) * L.w_out * 16;   // hi + lo planes
+    if (out_bytes > max_planes_bytes) max_planes_bytes = out_bytes;
+    if (l == 0) continue;
+    if (L.cin % 8 != 0 || L.cout % 8 != 0 || L.sw != 1 || L.w_out > G_ROWS)
+      OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "tensor-core leg: layer %s shape not supported", L.name);
+    const LayerWeights& w = h->host_w[L.name];
+    // three-term split product  x*w ~= xh*wh + xl*wh + xh*wl  (x = xh + xl, w = wh + wl in fp16):
+    // every (dh, dw, c8) tap becomes three copies (A plane hi/lo/hi, B rows wh/wh/wl)
+    const int c8in = L.cin / 8, nt = L.cout > 64 ? 128 : 64;
+    const int E0 = L.kh * L.kw * c8in, E = 3 * E0, n_slabs = (E + 3) / 4;
+    std::vector<int> cp(n_slabs * 4, 0), cs(n_slabs * 4, 0);
+    std::vector<__half> bp((size_t)n_slabs * 4 * nt * 8, __float2half(0.f));
+    for (int e0 = 0; e0 < E0; ++e0) {
+      const int c8 = e0 % c8in, dw = (e0 / c8in) % L.kw, dh = e0 / (c8in * L.kw);
+      for (int term = 0; term < 3; ++term) {
+        const int e = e0 * 3 + term;
+        cp[e] = dh * (2 * c8in) + (term == 1 ? c8in : 0) + c8;      // planes per input row: [hi c8in][lo c8in]
+        cs[e] = dw;
+        for (int n = 0; n < L.cout; ++n)
+          for (int k = 0; k < 8; ++k) {
+            const float wf = w.kernel[(((size_t)dh * L.kw + dw) * L.cin + c8 * 8 + k) * L.cout + n];
+            const __half wh = __float2half(wf);
+            const __half wl = __float2half(wf - __half2float(wh));
+            bp[((size_t)e * nt + n) * 8 + k] = (term == 2) ? wl : wh;
+          }
+      }
+    }
+    t->leg_slabs[l] = n_slabs;
+    t->leg_nt[l] = nt;
+    int rc2;
+    if ((rc2 = upload_vec(h, &t->wleg[l], bp)) != OVN_OK) return rc2;
+    if ((rc2 = upload_vec(h, &t->leg_plane[l], cp)) != OVN_OK) return rc2;
+    if ((rc2 = upload_vec(h, &t->leg_shift[l], cs)) != OVN_OK) return rc2;
+  }
+  for (int b = 0; b < 2; ++b) {
+    const size_t bytes = max_planes_bytes * h->cfg.max_batch_scans + 32768;   // + tile overrun slack
+    OVN_CUDA(h, cudaMalloc(&t->actp[b], bytes));
+    OVN_CUDA(h, cudaMemset(t->actp[b], 0, bytes));
+  }
   const int64_t maxp = h->cfg.max_batch_pairs;
   t->rows_pad = maxp * PAIR_ROWS + 1024;           // tile overrun (512) + window shift (50) slack
-  OVN_CUDA(h, cudaMalloc(&t->l16, (size_t)maxp * WF * CF * sizeof(__half)));
-  OVN_CUDA(h, cudaMalloc(&t->r16, (size_t)maxp * WF * CF * sizeof(__half)));
+  OVN_CUDA(h, cudaMalloc(&t->l16, (size_t)maxp * WF * K4_PITCH * sizeof(__half)));
+  OVN_CUDA(h, cudaMalloc(&t->r16, (size_t)maxp * WF * K4_PITCH * sizeof(__half)));
+  OVN_CUDA(h, cudaMemset(t->l16, 0, (size_t)maxp * WF * K4_PITCH * sizeof(__half)));
+  OVN_CUDA(h, cudaMemset(t->r16, 0, (size_t)maxp * WF * K4_PITCH * sizeof(__half)));
   OVN_CUDA(h, cudaMalloc(&t->o1, (size_t)120 * t->rows_pad * 8 * sizeof(__half)));
   OVN_CUDA(h, cudaMalloc(&t->x3, (size_t)16 * t->rows_pad * 8 * sizeof(__half)));
   OVN_CUDA(h, cudaMalloc(&t->partial, (size_t)t->rows_pad * 2 * sizeof(float)));
+  OVN_CUDA(h, cudaMalloc(&t->lc, (size_t)maxp * C6_VOL_L_BYTES));
+  OVN_CUDA(h, cudaMalloc(&t->rc, (size_t)maxp * C6_VOL_R_BYTES));
+  OVN_CUDA(h, cudaMalloc(&t->corr_part, (size_t)maxp * 2 * WF * sizeof(float)));
+  OVN_CUDA(h, cudaFuncSetAttribute(k_corr_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(C6Smem)));
   OVN_CUDA(h, cudaMalloc(&t->d_err, sizeof(int)));
   OVN_CUDA(h, cudaMemset(t->d_err, 0, sizeof(int)));
   OVN_CUDA(h, cudaMemset(t->o1, 0, (size_t)120 * t->rows_pad * 8 * sizeof(__half)));
   OVN_CUDA(h, cudaMemset(t->x3, 0, (size_t)16 * t->rows_pad * 8 * sizeof(__half)));
   OVN_CUDA(h, cudaFuncSetAttribute(k_delta_conv1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem)));
-  OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmem)));
-  OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmem)));
+  OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmem)));
+  OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmem)));
+  OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmem)));
+  OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmem)));
+  OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmem)));
   return OVN_OK;
 }
 
+// fp32 NHWC [n][H][W][C] -> hi/lo fp16 C8-interleaved planes [n][H][hi,lo][C/8][W][8]
+__global__ void __launch_bounds__(256)
+k_nhwc_to_planes(const float* __restrict__ x, int64_t total_chunks, int H, int W, int C8, __half* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (img, h, c8, w)
+  if (i >= total_chunks) return;
+  const int w = (int)(i % W);
+  int64_t r = i / W;
+  const int c8 = (int)(r % C8); r /= C8;                                   // r = img*H + h
+  const float* src = x + (r * W + w) * (int64_t)(C8 * 8) + c8 * 8;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(src + 4));
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  __half hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    hi[e] = __float2half_rn(v[e]);
+    lo[e] = __float2half_rn(v[e] - __half2float(hi[e]));
+  }
+  const int64_t plane_hi = r * (2 * C8) + c8;
+  *reinterpret_cast<uint4*>(out + ((size_t)plane_hi * W + w) * 8) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(out + ((size_t)(plane_hi + C8) * W + w) * 8) = *reinterpret_cast<const uint4*>(lo);
+}
+
 int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cudaStream_t s) {
-  // round 1: the leg runs on the fp32 SIMT kernels in both precision modes (one scan per query
-  // in the 1 x N search; the tcgen05 leg is the next step)
-  return leg_forward_fp32(h, d_input, n, d_fv, s);
+  // layer 1 (C_in = 4..25, stride (2,2)) stays on the fp32 SIMT kernel; layers 2..10 run on
+  // k_gemm_stream_tc over C8-interleaved fp16 activation planes: one CTA per output image row,
+  // the kw taps are row shifts of the bulk copies, the kh taps select the input row's planes.
+  TcState* t = h->tc;
+  if (!t) OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "tensor-core weights not packed");
+  prof_mark(h, PROF_LEG, s);
+  int rc = leg_layer_fp32(h, 0, d_input, h->d_act[0], n, s);
+  if (rc != OVN_OK) return rc;
+  {
+    const ConvSpec& L = h->leg[0];
+    const int64_t chunks = (int64_t)n * L.h_out * (L.cout / 8) * L.w_out;
+    k_nhwc_to_planes<<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(h->d_act[0], chunks, L.h_out, L.w_out,
+                                                                     L.cout / 8, t->actp[0]);
+    OVN_LAUNCH_CHECK(h);
+  }
+  int cur = 0;
+  for (int l = 1; l < h->n_leg; ++l) {
+    const ConvSpec& L = h->leg[l];
+    const bool last = (l == h->n_leg - 1);
+    GemmArgs a = {};
+    a.A = t->actp[cur]; a.a_pitch = L.w_in;
+    a.copy_plane = t->leg_plane[l]; a.copy_shift = t->leg_shift[l]; a.n_slabs = t->leg_slabs[l];
+    a.Bp = t->wleg[l]; a.bias = h->d_b[l]; a.M = L.w_out;
+    a.runs_per_img = L.h_out; a.in_img_planes = L.h_in * 2 * (L.cin / 8); a.in_run_planes = L.sh * 2 * (L.cin / 8);
+    a.out_planes = t->actp[cur ^ 1]; a.out_pitch = L.w_out; a.out_run_planes = 2 * (L.cout / 8);
+    a.out_f32 = d_fv;
+    a.n_valid = L.cout;
+    const dim3 grid(1, (unsigned)(n * L.h_out), 1);
+    if (last) {
+      if (L.cout != 128 || L.h_out != 1) OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "tensor-core leg: unexpected last layer");
+      k_gemm_stream_tc<3, 128><<<grid, G_THREADS, sizeof(GSmem), s>>>(a, t->d_err);
+    } else if (t->leg_nt[l] == 128) {
+      k_gemm_stream_tc<4, 128><<<grid, G_THREADS, sizeof(GSmem), s>>>(a, t->d_err);
+    } else {
+      k_gemm_stream_tc<4, 64><<<grid, G_THREADS, sizeof(GSmem), s>>>(a, t->d_err);
+    }
+    OVN_LAUNCH_CHECK(h);
+    cur ^= 1;
+  }
+  prof_mark(h, PROF_LEG, s);
+  return OVN_OK;
 }
 
 int tc_check_error(ovn_handle* h, cudaStream_t s) {
@@ -597,29 +1102,50 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query, c
     const int64_t M = (int64_t)np * PAIR_ROWS;
     const unsigned gx = (unsigned)((M + G_ROWS - 1) / G_ROWS);
     GemmArgs a2 = {};
-    a2.A = t->o1; a2.rows_pad = t->rows_pad; a2.slab_plane = t->slab2_plane; a2.slab_shift = t->slab2_shift;
+    a2.A = t->o1; a2.a_pitch = t->rows_pad; a2.copy_plane = t->slab2_plane; a2.copy_shift = t->slab2_shift;
     a2.n_slabs = 30; a2.Bp = t->w2p; a2.bias = h->d_b[base + 1]; a2.M = M;
-    a2.out_planes = t->x3; a2.out_rows_pad = t->rows_pad;
+    a2.runs_per_img = 1; a2.in_img_planes = 0; a2.in_run_planes = 0;
+    a2.out_planes = t->x3; a2.out_pitch = t->rows_pad; a2.out_run_planes = 16;
     prof_mark(h, PROF_CONV2, s);
-    k_gemm_stream_tc<1><<<dim3(gx, 1), G_THREADS, sizeof(GSmem), s>>>(a2, t->d_err);
+    k_gemm_stream_tc<1, 128><<<dim3(gx, 1, 1), G_THREADS, sizeof(GSmem), s>>>(a2, t->d_err);
     prof_mark(h, PROF_CONV2, s);
     OVN_LAUNCH_CHECK(h);
     GemmArgs a3 = {};
-    a3.A = t->x3; a3.rows_pad = t->rows_pad; a3.slab_plane = t->slab3_plane; a3.slab_shift = t->slab3_shift;
+    a3.A = t->x3; a3.a_pitch = t->rows_pad; a3.copy_plane = t->slab3_plane; a3.copy_shift = t->slab3_shift;
     a3.n_slabs = 36; a3.Bp = t->w3p; a3.bias = h->d_b[base + 2]; a3.M = M;
+    a3.runs_per_img = 1; a3.in_img_planes = 0; a3.in_run_planes = 0;
     a3.wd = h->d_w[base + 3]; a3.partial = t->partial; a3.grid_w = NB; a3.valid_w = NB - 2; a3.valid_h = NB - 2;
     a3.n_total = 256;
     prof_mark(h, PROF_CONV3, s);
-    k_gemm_stream_tc<2><<<dim3(gx, 2), G_THREADS, sizeof(GSmem), s>>>(a3, t->d_err);
+    k_gemm_stream_tc<2, 128><<<dim3(gx, 1, 2), G_THREADS, sizeof(GSmem), s>>>(a3, t->d_err);
     prof_mark(h, PROF_CONV3, s);
     OVN_LAUNCH_CHECK(h);
     k_dense_finalize<<<np, 256, 0, s>>>(t->partial, h->d_b[base + 3], PAIR_ROWS, d_overlap + p0);
     OVN_LAUNCH_CHECK(h);
-    prof_mark(h, PROF_CORR, s);
-    int rc = corr_forward_fp32(h, d_bank, d_query, left, right, np, d_yaw + p0,
-                               d_corr ? d_corr + (int64_t)p0 * WF : nullptr, s);
-    prof_mark(h, PROF_CORR, s);
-    if (rc != OVN_OK) return rc;
+    // correlation head (tensor cores, hi/lo split operands)
+    {
+      const int64_t perL = 3 * 2 * 8 * 128, perR = 2 * 16 * 192;
+      k_pack_corr_L<<<(unsigned)((np * perL + 255) / 256), 256, 0, s>>>(d_bank, left, np, t->lc);
+      OVN_LAUNCH_CHECK(h);
+      if (d_query) {
+        if (p0 == 0) {
+          k_pack_corr_R<<<(unsigned)((perR + 255) / 256), 256, 0, s>>>(d_query, nullptr, 1, t->rc);
+          OVN_LAUNCH_CHECK(h);
+        }
+      } else {
+        k_pack_corr_R<<<(unsigned)((np * perR + 255) / 256), 256, 0, s>>>(d_bank, right, np, t->rc);
+        OVN_LAUNCH_CHECK(h);
+      }
+      int g6 = h->sm_count / 2;
+      if (g6 > np) g6 = np;
+      if (g6 < 1) g6 = 1;
+      prof_mark(h, PROF_CORR, s);
+      k_corr_tc<<<2 * g6, C6_THREADS, sizeof(C6Smem), s>>>(t->lc, t->rc, d_query ? 0 : 1, np, t->corr_part, t->d_err);
+      prof_mark(h, PROF_CORR, s);
+      OVN_LAUNCH_CHECK(h);
+      k_corr_finalize<<<np, 384, 0, s>>>(t->corr_part, d_corr ? d_corr + (int64_t)p0 * WF : nullptr, d_yaw + p0);
+      OVN_LAUNCH_CHECK(h);
+    }
   }
   static const bool debug_sync = getenv("OVN_DEBUG_SYNC") != nullptr;
   if (debug_sync) return tc_check_error(h, s);
