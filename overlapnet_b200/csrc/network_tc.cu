@@ -48,7 +48,8 @@ struct TcState {
   int* slab2_plane = nullptr; int* slab2_shift = nullptr;     // per-copy (n_slabs*4) tables
   int* slab3_plane = nullptr; int* slab3_shift = nullptr;
   // tensor-core leg (layers 2..): packed weights + copy tables per layer, ping-pong activation planes
-  __half* wleg[kMaxLegLayers] = {};
+  __half* wleg[kMaxLegLayers] = {};      // [1][n_slabs][4][NT][8]   (throughput mode)
+  __half* wleg64[kMaxLegLayers] = {};    // [cout/64][n_slabs][4][64][8] (latency mode)
   int* leg_plane[kMaxLegLayers] = {};
   int* leg_shift[kMaxLegLayers] = {};
   int leg_slabs[kMaxLegLayers] = {};
@@ -89,7 +90,8 @@ k_gather_rows_f16(const float* __restrict__ bank, const int32_t* __restrict__ id
 // ------------------------------------------------------------------------------------------------
 // k_delta_conv1_tc
 // ------------------------------------------------------------------------------------------------
-constexpr int K4_THREADS = 512;
+constexpr int K4_PROD_WARPS = 16;       // two groups of 8 (4 TMEM lane quarters x 2 K halves); group g owns steps with step % 2 == g
+constexpr int K4_THREADS = (8 + K4_PROD_WARPS) * 32;
 constexpr int K4_STAGES = 6;            // A ring: TMEM column slots
 constexpr int K4_BSLOTS = 24;           // B ring: shared-memory slots of W1 slices (decoupled, deep enough for L2 latency)
 constexpr int K4_TILES = 3;
@@ -97,13 +99,15 @@ constexpr int K4_ACOL0 = 192;           // TMEM columns: D = [0,192), A stages =
 constexpr int K4_STAGE_COLS = 48;
 constexpr int K4_STEPS = 60;            // 4 channel chunks x 15 dj per jb
 constexpr int K4_BSLICE = 4096;         // bytes of W1 per step: [4 k8][64 o][8]
+constexpr int K4_RWIN_BYTES = S15 * K4_PITCH * 2;   // the 15 RIGHT rows one jb touches
 
 struct K4Smem {
-  __half R[WF * K4_PITCH];
+  __half L[WF * K4_PITCH];
+  __half Rw[2][S15 * K4_PITCH];         // double-buffered RIGHT-row window (streamed per jb)
   __half B[K4_BSLOTS][K4_BSLICE / 2];
   float bias[64];
   uint64_t a_full[K4_STAGES], a_empty[K4_STAGES], b_full[K4_BSLOTS], b_empty[K4_BSLOTS];
-  uint64_t d_full, d_empty, r_full, r_empty;
+  uint64_t d_full, d_empty, l_full, l_empty, rw_full[2], rw_empty[2];
   uint32_t tmem_base;
 };
 
@@ -113,10 +117,12 @@ struct K4Smem {
     goto done;                                           \
   }
 
-// Measured on B200 (profiles/r1_*): with W1 slices sharing the 6-deep A ring the kernel was bound
-// by the L2 -> shared round trip of a slice (slot turnaround ~4000 clk); the W1 ring is therefore
-// separate and 24 deep, which needs the LEFT volume out of shared memory: producers read their
-// three LEFT rows' 16 channels straight from L2 into registers one (jb, chunk) ahead.
+// Measured on B200 (profiles/r1_*): (1) with W1 slices sharing the 6-deep A ring the kernel was
+// bound by the L2 -> shared round trip of a slice (slot turnaround ~4000 clk), so the W1 ring is
+// separate and 24 deep; (2) that only fits next to the LEFT volume if the RIGHT volume is not
+// resident: a jb touches just 15 RIGHT rows, which are streamed as a 4 KB double-buffered window;
+// (3) a producer warp's LDS -> ALU -> tcgen05.st -> wait::st -> arrive chain runs at IPC ~0.2, so
+// 16 producer warps in two groups work on alternating steps.
 __global__ void __launch_bounds__(K4_THREADS, 1)
 k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16, int r_per_pair,
                  const __half* __restrict__ W1p, const float* __restrict__ bias1, __half* __restrict__ o1,
@@ -129,7 +135,8 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
     for (int s = 0; s < K4_STAGES; ++s) { mbar_init(&S.a_full[s], 8); mbar_init(&S.a_empty[s], 1); }
     for (int s = 0; s < K4_BSLOTS; ++s) { mbar_init(&S.b_full[s], 1); mbar_init(&S.b_empty[s], 1); }
     mbar_init(&S.d_full, 1); mbar_init(&S.d_empty, 4);
-    mbar_init(&S.r_full, 1); mbar_init(&S.r_empty, 8);
+    mbar_init(&S.l_full, 1); mbar_init(&S.l_empty, K4_PROD_WARPS);
+    for (int b = 0; b < 2; ++b) { mbar_init(&S.rw_full[b], 1); mbar_init(&S.rw_empty[b], K4_PROD_WARPS); }
     mbar_fence_init();
   }
   if (tid < 64) S.bias[tid] = bias1[tid];
@@ -141,19 +148,10 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
   constexpr uint32_t VOL_BYTES = WF * K4_PITCH * 2;
 
   if (warp == 0) {
-    // ===================== loader: R once (or per pair), W1 slices through the deep ring =======
+    // ===================== loader A: W1 slices through the deep ring ===========================
     if (lane == 0) {
-      if (!r_per_pair) {
-        mbar_arrive_expect_tx(&S.r_full, VOL_BYTES);
-        bulk_g2s(S.R, R16, VOL_BYTES, &S.r_full);
-      }
-      uint32_t pi = 0, bs = 0, bph = 0;
-      for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++pi) {
-        if (r_per_pair) {
-          TC_WAIT(&S.r_empty, (pi & 1) ^ 1, 101);
-          mbar_arrive_expect_tx(&S.r_full, VOL_BYTES);
-          bulk_g2s(S.R, R16 + (size_t)p * WF * K4_PITCH, VOL_BYTES, &S.r_full);
-        }
+      uint32_t bs = 0, bph = 0;
+      for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
         for (int jb = 0; jb < NB; ++jb) {
           for (int st = 0; st < K4_STEPS; ++st) {
             TC_WAIT(&S.b_empty[bs], bph ^ 1, 102);
@@ -161,6 +159,23 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
             bulk_g2s(S.B[bs], W1p + (size_t)st * (K4_BSLICE / 2), K4_BSLICE, &S.b_full[bs]);
             if (++bs == K4_BSLOTS) { bs = 0; bph ^= 1; }
           }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== loader B: LEFT volume per pair, RIGHT row window per jb ==============
+    if (lane == 0) {
+      uint32_t pi = 0, jbit = 0;
+      for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++pi) {
+        TC_WAIT(&S.l_empty, (pi & 1) ^ 1, 101);
+        mbar_arrive_expect_tx(&S.l_full, VOL_BYTES);
+        bulk_g2s(S.L, L16 + (size_t)p * WF * K4_PITCH, VOL_BYTES, &S.l_full);
+        const __half* Rp = R16 + (r_per_pair ? (size_t)p * WF * K4_PITCH : 0);
+        for (int jb = 0; jb < NB; ++jb, ++jbit) {
+          const uint32_t b = jbit & 1;
+          TC_WAIT(&S.rw_empty[b], ((jbit >> 1) & 1) ^ 1, 103);
+          mbar_arrive_expect_tx(&S.rw_full[b], K4_RWIN_BYTES);
+          bulk_g2s(S.Rw[b], Rp + (size_t)jb * S15 * K4_PITCH, K4_RWIN_BYTES, &S.rw_full[b]);
         }
       }
     }
@@ -223,29 +238,28 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
           const int i = t * 128 + q * 32 + lane;
           const int ib = i / S15, di = i - ib * S15;
           const int64_t m = (int64_t)p * PAIR_ROWS + ib * NB + jb;
-          uint32_t v[4][16];
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + t * 64 + c * 32, v);
+            tmem_ld_wait();
+            if (t == K4_TILES - 1 && c == 1) {   // everything is in registers: hand D back before the stores
+              fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&S.d_empty);
+            }
+            if (i < WF) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * 64 + c * 16, v[c]);
-          tmem_ld_wait();
-          if (t == K4_TILES - 1) {             // everything is in registers: hand D back before the stores
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.d_empty);
-          }
-          if (i < WF) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-#pragma unroll
-              for (int h8 = 0; h8 < 2; ++h8) {
+              for (int h8 = 0; h8 < 4; ++h8) {
                 uint32_t pk[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const int o = c * 16 + h8 * 8 + 2 * j;
-                  __half2 hh = __floats2half2_rn(__uint_as_float(v[c][h8 * 8 + 2 * j]) + S.bias[o],
-                                                 __uint_as_float(v[c][h8 * 8 + 2 * j + 1]) + S.bias[o + 1]);
+                  const int o = c * 32 + h8 * 8 + 2 * j;
+                  __half2 hh = __floats2half2_rn(__uint_as_float(v[h8 * 8 + 2 * j]) + S.bias[o],
+                                                 __uint_as_float(v[h8 * 8 + 2 * j + 1]) + S.bias[o + 1]);
                   pk[j] = *reinterpret_cast<uint32_t*>(&hh);
                 }
-                const int k8 = di * 8 + c * 2 + h8;               // plane = (di, o/8)
+                const int k8 = di * 8 + c * 4 + h8;               // plane = (di, o/8)
                 *reinterpret_cast<uint4*>(o1 + ((size_t)k8 * rows_pad + m) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
             }
@@ -255,72 +269,68 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
     }
   } else if (warp >= 8) {
     // ===================== producers: |l - r| -> TMEM ==========================================
-    // 8 warps: TMEM lane quarter q, K half `half` (16 of the 32 channels of a step).  A thread owns
-    // LEFT rows q*32+lane (+128, +256); their 16 channels of the current chunk live in registers
-    // (prefetched from L2 one (jb, chunk) ahead), the RIGHT row comes by broadcast LDS.128.
-    const int pw = warp - 8, q = pw & 3, half = (pw >> 2) & 1;
+    // 16 warps = 2 groups x (4 TMEM lane quarters x 2 K halves).  A thread owns LEFT rows
+    // q*32+lane (+128, +256); their 16 channels of the current chunk live in registers, the RIGHT
+    // row comes by broadcast LDS.128 from the per-jb window.  Group g produces the steps with
+    // step % 2 == g into ring slots g, g+2, g+4.
+    const int pw = warp - 8, q = pw & 3, half = (pw >> 2) & 1, grp = pw >> 3;
     const int row0 = q * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + K4_ACOL0 + half * 8;
-    uint32_t pi = 0, sg = 0, ph = 0;
-    if (!r_per_pair) { TC_WAIT(&S.r_full, 0, 401); }
+    uint32_t pi = 0, jbit = 0, sg = grp, ph = 0;
     for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++pi) {
-      if (r_per_pair) { TC_WAIT(&S.r_full, pi & 1, 402); }
-      const __half* Lp = L16 + (size_t)p * WF * K4_PITCH;
-      uint32_t Ln[K4_TILES][8];               // next chunk's LEFT registers (prefetch)
-      auto fetch = [&](int cc) {
-#pragma unroll
-        for (int t = 0; t < K4_TILES; ++t) {
-          const int i = t * 128 + row0;
-          uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
-          if (i < WF) {
-            const uint4* src = reinterpret_cast<const uint4*>(Lp + (size_t)i * K4_PITCH + cc * 32 + half * 16);
-            a = __ldg(src);
-            b = __ldg(src + 1);
-          }
-          Ln[t][0] = a.x; Ln[t][1] = a.y; Ln[t][2] = a.z; Ln[t][3] = a.w;
-          Ln[t][4] = b.x; Ln[t][5] = b.y; Ln[t][6] = b.z; Ln[t][7] = b.w;
-        }
-      };
-      fetch(0);
+      TC_WAIT(&S.l_full, pi & 1, 402);
+      for (int jb = 0; jb < NB; ++jb, ++jbit) {
+        const uint32_t wb = jbit & 1;
+        TC_WAIT(&S.rw_full[wb], (jbit >> 1) & 1, 404);
 #pragma unroll 1
-      for (int u = 0; u < NB * 4; ++u) {       // u = jb*4 + cc
-        const int jb = u >> 2, cc = u & 3;
-        uint32_t Lr[K4_TILES][8];
-#pragma unroll
-        for (int t = 0; t < K4_TILES; ++t)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) Lr[t][j] = Ln[t][j];
-        fetch((cc + 1) & 3);                   // the chunk sequence repeats for every jb
-        const int ch = cc * 32 + half * 16;
-#pragma unroll 1
-        for (int dj = 0; dj < S15; ++dj) {
-          const __half* rrow = &S.R[(jb * S15 + dj) * K4_PITCH + ch];
-          const uint4 ra = *reinterpret_cast<const uint4*>(rrow);                  // broadcast LDS
-          const uint4 rb = *reinterpret_cast<const uint4*>(rrow + 8);
-          const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-          TC_WAIT(&S.a_empty[sg], ph ^ 1, 403);
-          fence_after_sync();
+        for (int cc = 0; cc < 4; ++cc) {
+          const int ch = cc * 32 + half * 16;
+          uint32_t Lr[K4_TILES][8];
 #pragma unroll
           for (int t = 0; t < K4_TILES; ++t) {
-            uint32_t o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              // |l - r|: subtract on the FMA pipe, clear both sign bits on the ALU pipe (LOP3)
-              const __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&Lr[t][j]),
-                                        *reinterpret_cast<const __half2*>(&rw[j]));
-              o[j] = *reinterpret_cast<const uint32_t*>(&d) & 0x7fff7fffu;
+            const int i = t * 128 + row0;
+            uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+            if (i < WF) {
+              a = *reinterpret_cast<const uint4*>(&S.L[i * K4_PITCH + ch]);
+              b = *reinterpret_cast<const uint4*>(&S.L[i * K4_PITCH + ch + 8]);
             }
-            tmem_st_x8(lane_addr + sg * K4_STAGE_COLS + t * 16, o);
+            Lr[t][0] = a.x; Lr[t][1] = a.y; Lr[t][2] = a.z; Lr[t][3] = a.w;
+            Lr[t][4] = b.x; Lr[t][5] = b.y; Lr[t][6] = b.z; Lr[t][7] = b.w;
           }
-          tmem_st_wait();
-          fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&S.a_full[sg]);
-          if (++sg == K4_STAGES) { sg = 0; ph ^= 1; }
+          // step = jb*60 + cc*15 + dj; this group takes step % 2 == grp  <=>  dj % 2 == (grp + cc) % 2
+#pragma unroll 1
+          for (int dj = (grp + cc) & 1; dj < S15; dj += 2) {
+            const __half* rrow = &S.Rw[wb][dj * K4_PITCH + ch];
+            const uint4 ra = *reinterpret_cast<const uint4*>(rrow);                  // broadcast LDS
+            const uint4 rb = *reinterpret_cast<const uint4*>(rrow + 8);
+            const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+            TC_WAIT(&S.a_empty[sg], ph ^ 1, 403);
+            fence_after_sync();
+#pragma unroll
+            for (int t = 0; t < K4_TILES; ++t) {
+              uint32_t o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                // |l - r|: subtract on the FMA pipe, clear both sign bits on the ALU pipe (LOP3)
+                const __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&Lr[t][j]),
+                                          *reinterpret_cast<const __half2*>(&rw[j]));
+                o[j] = *reinterpret_cast<const uint32_t*>(&d) & 0x7fff7fffu;
+              }
+              tmem_st_x8(lane_addr + sg * K4_STAGE_COLS + t * 16, o);
+            }
+            tmem_st_wait();
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.a_full[sg]);
+            sg += 2;
+            if (sg >= K4_STAGES) { sg -= K4_STAGES; ph ^= 1; }
+          }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.rw_empty[wb]);
       }
       __syncwarp();
-      if (r_per_pair && lane == 0) mbar_arrive(&S.r_empty);
+      if (lane == 0) mbar_arrive(&S.l_empty);
     }
   }
 done:
@@ -333,16 +343,26 @@ done:
 // k_gemm_stream_tc
 // ------------------------------------------------------------------------------------------------
 constexpr int G_THREADS = 256;
-constexpr int G_STAGES = 4;
-constexpr int G_ROWS = 512;                      // 4 row tiles of 128
-constexpr int G_A_BYTES = 4 * G_ROWS * 16;       // 4 planes x 512 rows x 16 B = 32 KB
-constexpr int G_B_BYTES_MAX = 4 * 128 * 16;      // 4 planes x N (<=128) x 16 B
 
+// TILES = 128-row tiles per CTA: 4 for throughput (W slabs are reused by four tiles, 4-deep ring
+// of 40 KB stages), 1 for latency (single-scan leg: 4x more CTAs, 12-deep ring of 12-16 KB stages
+// so that the L2 round trip of a slab is hidden by ring depth rather than by work per stage).
+template <int NT, int TILES>
+struct GCfg {
+  static constexpr int ROWS = TILES * 128;
+  static constexpr int A_BYTES = 4 * ROWS * 16;       // 4 planes x ROWS x 16 B
+  static constexpr int B_BYTES = 4 * NT * 16;         // 4 planes x NT x 16 B
+  static constexpr int STAGES = TILES == 4 ? 4 : 12;
+};
+
+template <int NT, int TILES>
 struct GSmem {
-  uint8_t A[G_STAGES][G_A_BYTES];
-  uint8_t B[G_STAGES][G_B_BYTES_MAX];
+  using C = GCfg<NT, TILES>;
+  uint8_t A[C::STAGES][C::A_BYTES];
+  uint8_t B[C::STAGES][C::B_BYTES];
   float bias[128];
-  uint64_t full[G_STAGES], empty[G_STAGES], d_full;
+  int2 tab[1024];               // (plane, shift) of every copy, staged once: the loader thread must not chase global loads
+  uint64_t full[C::STAGES], empty[C::STAGES], d_full;
   uint32_t tmem_base;
 };
 
@@ -372,12 +392,14 @@ struct GemmArgs {
   int n_valid;                // output channels actually present (<= NT); 0 = NT
 };
 
-template <int EPI, int NT>
+template <int EPI, int NT, int TILES>
 __global__ void __launch_bounds__(G_THREADS, 1)
 k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  GSmem& S = *reinterpret_cast<GSmem*>(smem_raw);
-  constexpr int B_BYTES = 4 * NT * 16;
+  using C = GCfg<NT, TILES>;
+  GSmem<NT, TILES>& S = *reinterpret_cast<GSmem<NT, TILES>*>(smem_raw);
+  constexpr int B_BYTES = C::B_BYTES, G_ROWS = C::ROWS, G_A_BYTES = C::A_BYTES, G_STAGES = C::STAGES;
+  constexpr uint32_t TMEM_COLS = (TILES * NT) <= 64 ? 64 : ((TILES * NT) <= 128 ? 128 : ((TILES * NT) <= 256 ? 256 : 512));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t row0 = (int64_t)blockIdx.x * G_ROWS;
   const int y = blockIdx.y, nh = blockIdx.z;
@@ -388,8 +410,9 @@ k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
     mbar_init(&S.d_full, 1);
     mbar_fence_init();
   }
-  if (tid < NT) S.bias[tid] = g.bias[nh * NT + tid];
-  if (warp == 2) tmem_alloc(&S.tmem_base, 512);
+  if (tid < NT) S.bias[tid] = (g.n_valid == 0 || nh * NT + tid < g.n_valid) ? g.bias[nh * NT + tid] : 0.f;
+  for (int e = tid; e < g.n_slabs * 4; e += G_THREADS) S.tab[e] = make_int2(g.copy_plane[e], g.copy_shift[e]);
+  if (warp == 2) tmem_alloc(&S.tmem_base, TMEM_COLS);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -403,8 +426,9 @@ k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
         mbar_arrive_expect_tx(&S.full[s], G_A_BYTES + B_BYTES);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int64_t plane = in_base + g.copy_plane[sl * 4 + j];
-          const int64_t r = row0 + g.copy_shift[sl * 4 + j];
+          const int2 ps = S.tab[sl * 4 + j];
+          const int64_t plane = in_base + ps.x;
+          const int64_t r = row0 + ps.y;
           bulk_g2s(S.A[s] + j * (G_ROWS * 16), g.A + ((size_t)plane * g.a_pitch + r) * 8, G_ROWS * 16, &S.full[s]);
         }
         bulk_g2s(S.B[s], g.Bp + ((size_t)nh * g.n_slabs + sl) * (B_BYTES / 2), B_BYTES, &S.full[s]);
@@ -424,9 +448,9 @@ k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
       TC_WAIT(&S.full[sg], ph, 502);
       fence_after_sync();
       if (leader) {
-        const uint32_t a_off = (sg * G_A_BYTES) >> 4, b_off = (sg * G_B_BYTES_MAX) >> 4;
+        const uint32_t a_off = (sg * G_A_BYTES) >> 4, b_off = (sg * B_BYTES) >> 4;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 0; t < TILES; ++t) {
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
             const uint64_t ad = ((uint64_t)ad_hi << 32) | (uint64_t)(ad_lo + a_off + ((t * 128 * 16 + kk * 2 * (G_ROWS * 16)) >> 4));
@@ -446,7 +470,7 @@ k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
     TC_WAIT(&S.d_full, 0, 503);
     fence_after_sync();
 #pragma unroll 1
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < TILES; ++t) {
       const int64_t r = row0 + t * 128 + q * 32 + lane;
       if (EPI == 1 || EPI == 3 || EPI == 4) {
 #pragma unroll 1
@@ -454,7 +478,7 @@ k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
           uint32_t v[16];
           tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * NT + c0, v);
           tmem_ld_wait();
-          if (r < g.M && (g.n_valid == 0 || c0 < g.n_valid)) {
+          if (r < g.M && (g.n_valid == 0 || nh * NT + c0 < g.n_valid)) {
             if (EPI == 4) {
               // bias + ReLU -> hi/lo fp16 split planes (x = hi + lo to 2^-22): the next layer's
               // three-term product keeps the leg at fp32-grade accuracy on the fp16 tensor pipe
@@ -472,7 +496,7 @@ k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
                   ph[j] = *reinterpret_cast<const uint32_t*>(&hi);
                   pl[j] = *reinterpret_cast<const uint32_t*>(&lo);
                 }
-                const int c8 = (c0 >> 3) + h8;
+                const int c8 = nh * (NT / 8) + (c0 >> 3) + h8;
                 const int64_t plane = (int64_t)y * g.out_run_planes + c8;
                 *reinterpret_cast<uint4*>(g.out_planes + ((size_t)plane * g.out_pitch + r) * 8) =
                     make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -495,7 +519,7 @@ k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
                     make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
             } else {
-              float* dst = g.out_f32 + ((size_t)y * g.M + r) * NT + c0;
+              float* dst = g.out_f32 + ((size_t)y * g.M + r) * (g.n_valid ? g.n_valid : NT) + nh * NT + c0;
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
                 float4 o;
@@ -539,7 +563,7 @@ k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
 done:
   fence_before_sync();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  if (warp == 2) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -851,6 +875,7 @@ void tc_free(ovn_handle* h) {
   for (void* b : bufs) if (b) cudaFree(b);
   for (int l = 0; l < kMaxLegLayers; ++l) {
     if (t->wleg[l]) cudaFree(t->wleg[l]);
+    if (t->wleg64[l]) cudaFree(t->wleg64[l]);
     if (t->leg_plane[l]) cudaFree(t->leg_plane[l]);
     if (t->leg_shift[l]) cudaFree(t->leg_shift[l]);
   }
@@ -931,7 +956,7 @@ int tc_pack_weights(ovn_handle* h) {
     const size_t out_bytes = (size_t)L.h_out * 2 * (L.cout / 8) * L.w_out * 16;   // hi + lo planes
     if (out_bytes > max_planes_bytes) max_planes_bytes = out_bytes;
     if (l == 0) continue;
-    if (L.cin % 8 != 0 || L.cout % 8 != 0 || L.sw != 1 || L.w_out > G_ROWS)
+    if (L.cin % 8 != 0 || L.cout % 8 != 0 || L.sw != 1 || L.w_out > 512)
       OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "tensor-core leg: layer %s shape not supported", L.name);
     const LayerWeights& w = h->host_w[L.name];
     // three-term split product  x*w ~= xh*wh + xl*wh + xh*wl  (x = xh + xl, w = wh + wl in fp16):
@@ -955,10 +980,19 @@ int tc_pack_weights(ovn_handle* h) {
           }
       }
     }
+    // the same weights sliced into 64-channel halves for the latency variant
+    const int nz = (L.cout + 63) / 64;
+    std::vector<__half> bp64((size_t)nz * n_slabs * 4 * 64 * 8, __float2half(0.f));
+    for (int z = 0; z < nz; ++z)
+      for (int e = 0; e < n_slabs * 4; ++e)
+        for (int n = 0; n < 64 && z * 64 + n < nt; ++n)
+          for (int k = 0; k < 8; ++k)
+            bp64[(((size_t)z * n_slabs * 4 + e) * 64 + n) * 8 + k] = bp[((size_t)e * nt + z * 64 + n) * 8 + k];
     t->leg_slabs[l] = n_slabs;
     t->leg_nt[l] = nt;
     int rc2;
     if ((rc2 = upload_vec(h, &t->wleg[l], bp)) != OVN_OK) return rc2;
+    if ((rc2 = upload_vec(h, &t->wleg64[l], bp64)) != OVN_OK) return rc2;
     if ((rc2 = upload_vec(h, &t->leg_plane[l], cp)) != OVN_OK) return rc2;
     if ((rc2 = upload_vec(h, &t->leg_shift[l], cs)) != OVN_OK) return rc2;
   }
@@ -985,11 +1019,13 @@ int tc_pack_weights(ovn_handle* h) {
   OVN_CUDA(h, cudaMemset(t->o1, 0, (size_t)120 * t->rows_pad * 8 * sizeof(__half)));
   OVN_CUDA(h, cudaMemset(t->x3, 0, (size_t)16 * t->rows_pad * 8 * sizeof(__half)));
   OVN_CUDA(h, cudaFuncSetAttribute(k_delta_conv1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem)));
-  OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmem)));
-  OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmem)));
-  OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmem)));
-  OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmem)));
-  OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmem)));
+#define OVN_GEMM_ATTR(E, N, T)                                                                                  \
+  OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<E, N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                   (int)sizeof(GSmem<N, T>)))
+  OVN_GEMM_ATTR(1, 128, 4); OVN_GEMM_ATTR(2, 128, 4);
+  OVN_GEMM_ATTR(4, 64, 4); OVN_GEMM_ATTR(4, 128, 4); OVN_GEMM_ATTR(3, 128, 4);
+  OVN_GEMM_ATTR(4, 64, 1); OVN_GEMM_ATTR(3, 64, 1);
+#undef OVN_GEMM_ATTR
   return OVN_OK;
 }
 
@@ -1044,14 +1080,20 @@ int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cuda
     a.out_planes = t->actp[cur ^ 1]; a.out_pitch = L.w_out; a.out_run_planes = 2 * (L.cout / 8);
     a.out_f32 = d_fv;
     a.n_valid = L.cout;
-    const dim3 grid(1, (unsigned)(n * L.h_out), 1);
-    if (last) {
-      if (L.cout != 128 || L.h_out != 1) OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "tensor-core leg: unexpected last layer");
-      k_gemm_stream_tc<3, 128><<<grid, G_THREADS, sizeof(GSmem), s>>>(a, t->d_err);
-    } else if (t->leg_nt[l] == 128) {
-      k_gemm_stream_tc<4, 128><<<grid, G_THREADS, sizeof(GSmem), s>>>(a, t->d_err);
+    // latency mode (few scans): one 128-row tile and one 64-channel slice per CTA, 12-deep ring;
+    // throughput mode (batched encode): four tiles per CTA share every weight slab
+    const bool latency = (int64_t)n * L.h_out * 4 <= h->sm_count;
+    if (last && (L.cout != 128 || L.h_out != 1)) OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "tensor-core leg: unexpected last layer");
+    if (latency) {
+      const dim3 grid((unsigned)((L.w_out + 127) / 128), (unsigned)(n * L.h_out), (unsigned)((L.cout + 63) / 64));
+      a.Bp = t->wleg64[l];
+      if (last) k_gemm_stream_tc<3, 64, 1><<<grid, G_THREADS, sizeof(GSmem<64, 1>), s>>>(a, t->d_err);
+      else k_gemm_stream_tc<4, 64, 1><<<grid, G_THREADS, sizeof(GSmem<64, 1>), s>>>(a, t->d_err);
     } else {
-      k_gemm_stream_tc<4, 64><<<grid, G_THREADS, sizeof(GSmem), s>>>(a, t->d_err);
+      const dim3 grid(1, (unsigned)(n * L.h_out), 1);
+      if (last) k_gemm_stream_tc<3, 128, 4><<<grid, G_THREADS, sizeof(GSmem<128, 4>), s>>>(a, t->d_err);
+      else if (t->leg_nt[l] == 128) k_gemm_stream_tc<4, 128, 4><<<grid, G_THREADS, sizeof(GSmem<128, 4>), s>>>(a, t->d_err);
+      else k_gemm_stream_tc<4, 64, 4><<<grid, G_THREADS, sizeof(GSmem<64, 4>), s>>>(a, t->d_err);
     }
     OVN_LAUNCH_CHECK(h);
     cur ^= 1;
@@ -1100,14 +1142,14 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query, c
     prof_mark(h, PROF_DELTA, s);
     OVN_LAUNCH_CHECK(h);
     const int64_t M = (int64_t)np * PAIR_ROWS;
-    const unsigned gx = (unsigned)((M + G_ROWS - 1) / G_ROWS);
+    const unsigned gx = (unsigned)((M + 511) / 512);
     GemmArgs a2 = {};
     a2.A = t->o1; a2.a_pitch = t->rows_pad; a2.copy_plane = t->slab2_plane; a2.copy_shift = t->slab2_shift;
     a2.n_slabs = 30; a2.Bp = t->w2p; a2.bias = h->d_b[base + 1]; a2.M = M;
     a2.runs_per_img = 1; a2.in_img_planes = 0; a2.in_run_planes = 0;
     a2.out_planes = t->x3; a2.out_pitch = t->rows_pad; a2.out_run_planes = 16;
     prof_mark(h, PROF_CONV2, s);
-    k_gemm_stream_tc<1, 128><<<dim3(gx, 1, 1), G_THREADS, sizeof(GSmem), s>>>(a2, t->d_err);
+    k_gemm_stream_tc<1, 128, 4><<<dim3(gx, 1, 1), G_THREADS, sizeof(GSmem<128, 4>), s>>>(a2, t->d_err);
     prof_mark(h, PROF_CONV2, s);
     OVN_LAUNCH_CHECK(h);
     GemmArgs a3 = {};
@@ -1117,7 +1159,7 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query, c
     a3.wd = h->d_w[base + 3]; a3.partial = t->partial; a3.grid_w = NB; a3.valid_w = NB - 2; a3.valid_h = NB - 2;
     a3.n_total = 256;
     prof_mark(h, PROF_CONV3, s);
-    k_gemm_stream_tc<2, 128><<<dim3(gx, 1, 2), G_THREADS, sizeof(GSmem), s>>>(a3, t->d_err);
+    k_gemm_stream_tc<2, 128, 4><<<dim3(gx, 1, 2), G_THREADS, sizeof(GSmem<128, 4>), s>>>(a3, t->d_err);
     prof_mark(h, PROF_CONV3, s);
     OVN_LAUNCH_CHECK(h);
     k_dense_finalize<<<np, 256, 0, s>>>(t->partial, h->d_b[base + 3], PAIR_ROWS, d_overlap + p0);
