@@ -90,10 +90,11 @@ k_gather_rows_f16(const float* __restrict__ bank, const int32_t* __restrict__ id
 // ------------------------------------------------------------------------------------------------
 // k_delta_conv1_tc
 // ------------------------------------------------------------------------------------------------
-constexpr int K4_PROD_WARPS = 16;       // two groups of 8 (4 TMEM lane quarters x 2 K halves); group g owns steps with step % 2 == g
+constexpr int K4_PROD_WARPS = 12;       // three groups of 4 warps (one per TMEM lane quarter); group g owns steps with step % 3 == g
 constexpr int K4_THREADS = (8 + K4_PROD_WARPS) * 32;
 constexpr int K4_STAGES = 6;            // A ring: TMEM column slots
-constexpr int K4_BSLOTS = 24;           // B ring: shared-memory slots of W1 slices (decoupled, deep enough for L2 latency)
+constexpr int K4_BGROUPS = 4;           // B ring: 4 groups of 6 consecutive W1 slices (24 KB, one bulk copy, one barrier each)
+constexpr int K4_BSLOTS = 24;
 constexpr int K4_TILES = 3;
 constexpr int K4_ACOL0 = 192;           // TMEM columns: D = [0,192), A stages = [192, 192 + 6*48)
 constexpr int K4_STAGE_COLS = 48;
@@ -106,7 +107,7 @@ struct K4Smem {
   __half Rw[2][S15 * K4_PITCH];         // double-buffered RIGHT-row window (streamed per jb)
   __half B[K4_BSLOTS][K4_BSLICE / 2];
   float bias[64];
-  uint64_t a_full[K4_STAGES], a_empty[K4_STAGES], b_full[K4_BSLOTS], b_empty[K4_BSLOTS];
+  uint64_t a_full[K4_STAGES], a_empty[K4_STAGES], b_full[K4_BGROUPS], b_empty[K4_BGROUPS];
   uint64_t d_full, d_empty, l_full, l_empty, rw_full[2], rw_empty[2];
   uint32_t tmem_base;
 };
@@ -132,8 +133,8 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int s = 0; s < K4_STAGES; ++s) { mbar_init(&S.a_full[s], 8); mbar_init(&S.a_empty[s], 1); }
-    for (int s = 0; s < K4_BSLOTS; ++s) { mbar_init(&S.b_full[s], 1); mbar_init(&S.b_empty[s], 1); }
+    for (int s = 0; s < K4_STAGES; ++s) { mbar_init(&S.a_full[s], 4); mbar_init(&S.a_empty[s], 1); }
+    for (int s = 0; s < K4_BGROUPS; ++s) { mbar_init(&S.b_full[s], 1); mbar_init(&S.b_empty[s], 1); }
     mbar_init(&S.d_full, 1); mbar_init(&S.d_empty, 4);
     mbar_init(&S.l_full, 1); mbar_init(&S.l_empty, K4_PROD_WARPS);
     for (int b = 0; b < 2; ++b) { mbar_init(&S.rw_full[b], 1); mbar_init(&S.rw_empty[b], K4_PROD_WARPS); }
@@ -148,16 +149,16 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
   constexpr uint32_t VOL_BYTES = WF * K4_PITCH * 2;
 
   if (warp == 0) {
-    // ===================== loader A: W1 slices through the deep ring ===========================
+    // ===================== loader A: W1 through the deep ring, 6 consecutive slices per copy ====
     if (lane == 0) {
-      uint32_t bs = 0, bph = 0;
+      uint32_t bg = 0, bph = 0;
       for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
         for (int jb = 0; jb < NB; ++jb) {
-          for (int st = 0; st < K4_STEPS; ++st) {
-            TC_WAIT(&S.b_empty[bs], bph ^ 1, 102);
-            mbar_arrive_expect_tx(&S.b_full[bs], K4_BSLICE);
-            bulk_g2s(S.B[bs], W1p + (size_t)st * (K4_BSLICE / 2), K4_BSLICE, &S.b_full[bs]);
-            if (++bs == K4_BSLOTS) { bs = 0; bph ^= 1; }
+          for (int o = 0; o < K4_STEPS / K4_STAGES; ++o) {
+            TC_WAIT(&S.b_empty[bg], bph ^ 1, 102);
+            mbar_arrive_expect_tx(&S.b_full[bg], K4_STAGES * K4_BSLICE);
+            bulk_g2s(S.B[bg * K4_STAGES], W1p + (size_t)o * K4_STAGES * (K4_BSLICE / 2), K4_STAGES * K4_BSLICE, &S.b_full[bg]);
+            if (++bg == K4_BGROUPS) { bg = 0; bph ^= 1; }
           }
         }
       }
@@ -189,7 +190,11 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
       const uint64_t bdesc0 = make_desc_kmajor_noswizzle(smem_u32(S.B[0]), 1024, 128);
       const uint32_t bd_hi = (uint32_t)(bdesc0 >> 32), bd_lo = (uint32_t)bdesc0;
       const bool leader = elect_one() != 0;
-      uint32_t jbit = 0, bs = 0, bph = 0;
+      // An mbarrier probe costs ~90 clk even when the phase is already complete, and this warp is the
+      // pacemaker: W1 is waited for once per 6 steps (one barrier per 24 KB group) and the A barrier
+      // of step s+1 is probed BEFORE the MMAs of step s are issued, so its latency hides behind them.
+      const uint32_t a_full0 = smem_u32(&S.a_full[0]);
+      uint32_t jbit = 0, bg = 0, bph = 0;
       for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
         for (int jb = 0; jb < NB; ++jb, ++jbit) {
           TC_WAIT(&S.d_empty, (jbit & 1) ^ 1, 201);
@@ -197,28 +202,30 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
 #pragma unroll 1
           for (uint32_t o = 0; o < K4_STEPS / K4_STAGES; ++o) {
             const uint32_t ph = o & 1;            // (step / 6) & 1: steps per jb (60) and per pair are multiples of 12
+            TC_WAIT(&S.b_full[bg], bph, 203);
+            bool ready = mbar_try_wait_addr(a_full0, ph);
+            const uint32_t b_lo = bd_lo + ((bg * K4_STAGES * K4_BSLICE) >> 4);
 #pragma unroll
             for (int sg = 0; sg < K4_STAGES; ++sg) {
-              TC_WAIT(&S.a_full[sg], ph, 202);
-              TC_WAIT(&S.b_full[bs], bph, 203);
+              if (!ready) { if (!mbar_wait_addr(a_full0 + sg * 8, ph, kWaitCycles)) { atomicExch(err, 202); goto done; } }
+              if (sg + 1 < K4_STAGES) ready = mbar_try_wait_addr(a_full0 + (sg + 1) * 8, ph);   // probe ahead
               fence_after_sync();
               if (leader) {
-                const uint32_t b_lo = bd_lo + ((bs * K4_BSLICE) >> 4);
 #pragma unroll
                 for (int t = 0; t < K4_TILES; ++t) {
 #pragma unroll
                   for (int kk = 0; kk < 2; ++kk) {
-                    const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_lo + ((kk * 2048) >> 4));
+                    const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_lo + ((sg * K4_BSLICE + kk * 2048) >> 4));
                     mma_ts(tmem + t * 64, tmem + K4_ACOL0 + sg * K4_STAGE_COLS + t * 16 + kk * 8, bd, idesc,
                            (o | (uint32_t)sg | (uint32_t)kk) != 0);
                   }
                 }
                 commit(&S.a_empty[sg]);
-                commit(&S.b_empty[bs]);
+                if (sg == K4_STAGES - 1) commit(&S.b_empty[bg]);
               }
               __syncwarp();
-              if (++bs == K4_BSLOTS) { bs = 0; bph ^= 1; }
             }
+            if (++bg == K4_BGROUPS) { bg = 0; bph ^= 1; }
           }
           if (leader) commit(&S.d_full);
           __syncwarp();
@@ -269,14 +276,17 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
     }
   } else if (warp >= 8) {
     // ===================== producers: |l - r| -> TMEM ==========================================
-    // 16 warps = 2 groups x (4 TMEM lane quarters x 2 K halves).  A thread owns LEFT rows
-    // q*32+lane (+128, +256); their 16 channels of the current chunk live in registers, the RIGHT
-    // row comes by broadcast LDS.128 from the per-jb window.  Group g produces the steps with
-    // step % 2 == g into ring slots g, g+2, g+4.
-    const int pw = warp - 8, q = pw & 3, half = (pw >> 2) & 1, grp = pw >> 3;
+    // 12 warps = 3 groups x 4 TMEM lane quarters.  A thread owns LEFT rows q*32+lane (+128, +256);
+    // all 32 channels of the current chunk live in registers (48), the RIGHT row comes by broadcast
+    // LDS.128 from the per-jb window.  Group g produces the steps with step % 3 == g (15 and 60 are
+    // multiples of 3: dj = g, g+3, ...) into ring slots g, g+3: per synthesised element this costs
+    // 1 ALU instruction + ~0.3 of loop / barrier overhead, and a group has three MMA stage-times
+    // to hide its LDS -> ALU -> tcgen05.st -> wait::st -> arrive chain.
+    const int pw = warp - 8, q = pw & 3, grp = pw >> 2;
     const int row0 = q * 32 + lane;
-    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + K4_ACOL0 + half * 8;
-    uint32_t pi = 0, jbit = 0, sg = grp, ph = 0;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + K4_ACOL0;
+    const uint32_t a_empty0 = smem_u32(&S.a_empty[0]), a_full0 = smem_u32(&S.a_full[0]);
+    uint32_t pi = 0, jbit = 0, n = 0;       // n: steps produced by this group: slot = grp + 3*(n&1), phase = (n>>1)&1
     for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++pi) {
       TC_WAIT(&S.l_full, pi & 1, 402);
       for (int jb = 0; jb < NB; ++jb, ++jbit) {
@@ -284,46 +294,46 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
         TC_WAIT(&S.rw_full[wb], (jbit >> 1) & 1, 404);
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
-          const int ch = cc * 32 + half * 16;
-          uint32_t Lr[K4_TILES][8];
+          const int ch = cc * 32;
+          uint32_t Lr[K4_TILES][16];
 #pragma unroll
           for (int t = 0; t < K4_TILES; ++t) {
             const int i = t * 128 + row0;
-            uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
-            if (i < WF) {
-              a = *reinterpret_cast<const uint4*>(&S.L[i * K4_PITCH + ch]);
-              b = *reinterpret_cast<const uint4*>(&S.L[i * K4_PITCH + ch + 8]);
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) {
+              uint4 a = make_uint4(0u, 0u, 0u, 0u);
+              if (i < WF) a = *reinterpret_cast<const uint4*>(&S.L[i * K4_PITCH + ch + v4 * 8]);
+              Lr[t][v4 * 4 + 0] = a.x; Lr[t][v4 * 4 + 1] = a.y; Lr[t][v4 * 4 + 2] = a.z; Lr[t][v4 * 4 + 3] = a.w;
             }
-            Lr[t][0] = a.x; Lr[t][1] = a.y; Lr[t][2] = a.z; Lr[t][3] = a.w;
-            Lr[t][4] = b.x; Lr[t][5] = b.y; Lr[t][6] = b.z; Lr[t][7] = b.w;
           }
-          // step = jb*60 + cc*15 + dj; this group takes step % 2 == grp  <=>  dj % 2 == (grp + cc) % 2
 #pragma unroll 1
-          for (int dj = (grp + cc) & 1; dj < S15; dj += 2) {
+          for (int dj = grp; dj < S15; dj += 3, ++n) {
+            const uint32_t sg = grp + 3 * (n & 1), ph = (n >> 1) & 1;
             const __half* rrow = &S.Rw[wb][dj * K4_PITCH + ch];
-            const uint4 ra = *reinterpret_cast<const uint4*>(rrow);                  // broadcast LDS
-            const uint4 rb = *reinterpret_cast<const uint4*>(rrow + 8);
-            const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-            TC_WAIT(&S.a_empty[sg], ph ^ 1, 403);
+            if (!mbar_wait_addr(a_empty0 + sg * 8, ph ^ 1, kWaitCycles)) { atomicExch(err, 403); goto done; }
             fence_after_sync();
 #pragma unroll
-            for (int t = 0; t < K4_TILES; ++t) {
-              uint32_t o[8];
+            for (int hk = 0; hk < 2; ++hk) {          // two 16-channel halves: keeps the live set of r at 8 registers
+              const uint4 ra = *reinterpret_cast<const uint4*>(rrow + hk * 16);        // broadcast LDS
+              const uint4 rb = *reinterpret_cast<const uint4*>(rrow + hk * 16 + 8);
+              const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                // |l - r|: subtract on the FMA pipe, clear both sign bits on the ALU pipe (LOP3)
-                const __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&Lr[t][j]),
-                                          *reinterpret_cast<const __half2*>(&rw[j]));
-                o[j] = *reinterpret_cast<const uint32_t*>(&d) & 0x7fff7fffu;
+              for (int t = 0; t < K4_TILES; ++t) {
+                uint32_t o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  // |l - r|: subtract on the FMA pipe, clear both sign bits on the ALU pipe (LOP3)
+                  const __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&Lr[t][hk * 8 + j]),
+                                            *reinterpret_cast<const __half2*>(&rw[j]));
+                  o[j] = *reinterpret_cast<const uint32_t*>(&d) & 0x7fff7fffu;
+                }
+                tmem_st_x8(lane_addr + sg * K4_STAGE_COLS + t * 16 + hk * 8, o);
               }
-              tmem_st_x8(lane_addr + sg * K4_STAGE_COLS + t * 16, o);
             }
             tmem_st_wait();
             fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&S.a_full[sg]);
-            sg += 2;
-            if (sg >= K4_STAGES) { sg -= K4_STAGES; ph ^= 1; }
+            if (lane == 0) mbar_arrive_addr(a_full0 + sg * 8);
           }
         }
         __syncwarp();

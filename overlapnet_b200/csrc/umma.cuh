@@ -142,6 +142,26 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, long l
   return true;
 }
 
+// Address-based variants (precomputed 32-bit shared addresses: keeps cvta out of inner loops)
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait_addr(uint32_t bar, uint32_t parity, long long max_cycles) {
+  if (mbar_try_wait_addr(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_addr(bar, parity)) {
+    if (clock64() - t0 > max_cycles) return false;
+  }
+  return true;
+}
+
 // ---- bulk async copy global -> shared (TMA engine, 1-D), completes on an mbarrier ---------------
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
