@@ -156,6 +156,16 @@ int ovn_heads_1vsN(ovn_handle* h, const float* d_bank, int64_t bank_size, const 
                    const int32_t* d_cand_idx, int32_t n_cand,
                    float* d_overlap, int32_t* d_yaw, float* d_corr, void* stream);
 
+/* ---- resident bank (Infer keeps self.feature_volumes across calls, infer.py:113,184-193) ---------
+ * The tensor-core heads consume fp16 / hi-lo split copies of the LEFT volumes.  Without this call
+ * they are rebuilt from d_bank on every heads call; ovn_bank_prepare builds them once for rows
+ * [first, first+count) of the bank that lives at d_bank (capacity = rows the bank may grow to), and
+ * every later ovn_heads_forward / ovn_heads_1vsN whose d_bank is the same pointer reuses them.
+ * Call it again for rows that were appended or overwritten.  No-op for precision fp32. */
+int ovn_bank_prepare(ovn_handle* h, const float* d_bank, int64_t bank_capacity, int64_t first, int64_t count,
+                     void* stream);
+int ovn_bank_release(ovn_handle* h, const float* d_bank);
+
 /* ---- host-buffer convenience entry points (what a non-CUDA caller binds; bench.py e2e) ------ */
 /* Raw clouds on the host -> feature volumes on the host. */
 int ovn_encode_clouds_host(ovn_handle* h, const float* h_points, const int64_t* h_offsets,

@@ -16,7 +16,7 @@ SYMBOLS = [
     'ovn_abi_version', 'ovn_input_channels', 'ovn_feature_width', 'ovn_feature_channels',
     'ovn_launch_count', 'ovn_profile_enable', 'ovn_profile_read', 'ovn_set_weights', 'ovn_finalize_weights', 'ovn_project_batch',
     'ovn_normals_batch', 'ovn_semantic_batch', 'ovn_preprocess_batch', 'ovn_pack_input',
-    'ovn_leg_forward', 'ovn_heads_forward', 'ovn_heads_1vsN', 'ovn_encode_clouds_host',
+    'ovn_leg_forward', 'ovn_heads_forward', 'ovn_heads_1vsN', 'ovn_bank_prepare', 'ovn_bank_release', 'ovn_encode_clouds_host',
     'ovn_query_cloud_vs_bank_host',
 ]
 
@@ -79,6 +79,8 @@ def lib():
   L.ovn_leg_forward.argtypes = [vp, vp, i32, vp, vp]
   L.ovn_heads_forward.argtypes = [vp, vp, i64, vp, vp, i32, vp, vp, vp, vp]
   L.ovn_heads_1vsN.argtypes = [vp, vp, i64, vp, vp, i32, vp, vp, vp, vp]
+  L.ovn_bank_prepare.argtypes = [vp, vp, i64, i64, i64, vp]
+  L.ovn_bank_release.argtypes = [vp, vp]
   L.ovn_encode_clouds_host.argtypes = [vp, vp, vp, i32, vp]
   L.ovn_query_cloud_vs_bank_host.argtypes = [vp, vp, i64, vp, i64, vp, i32, vp, vp, vp]
   _lib = L

@@ -20,9 +20,9 @@ static void set_spec(ConvSpec& L, const char* name, int kh, int kw, int sh, int 
   L.w_out = (w_in - kw) / sw + 1;
 }
 
-static __global__ void k_iota(int32_t* p, int n) {
+static __global__ void k_iota(int32_t* p, int n, int start) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = i;
+  if (i < n) p[i] = start + i;
 }
 
 extern "C" {
@@ -413,14 +413,30 @@ int ovn_heads_1vsN(ovn_handle* h, const float* d_bank, int64_t bank_size, const 
   const int maxp = h->cfg.max_batch_pairs;
   for (int p0 = 0; p0 < n_cand; p0 += maxp) {
     const int np = (n_cand - p0 < maxp) ? n_cand - p0 : maxp;
-    k_iota<<<(np + 255) / 256, 256, 0, s>>>(h->d_idx_tmp, np);
+    k_iota<<<(np + 255) / 256, 256, 0, s>>>(h->d_idx_tmp, np, p0);
     OVN_LAUNCH_CHECK(h);
-    int rc = heads_dispatch(h, d_bank + (size_t)p0 * h->cfg.leg_output_width * kFeatC, d_query, h->d_idx_tmp, nullptr,
+    int rc = heads_dispatch(h, d_bank, d_query, h->d_idx_tmp, nullptr,
                             np, d_overlap + p0, d_yaw + p0,
                             d_corr ? d_corr + (size_t)p0 * h->cfg.leg_output_width : nullptr, s);
     if (rc != OVN_OK) return rc;
   }
   return OVN_OK;
+}
+
+int ovn_bank_prepare(ovn_handle* h, const float* d_bank, int64_t bank_capacity, int64_t first, int64_t count,
+                     void* stream) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  REQUIRE(h, d_bank != nullptr, "d_bank is NULL");
+  REQUIRE(h, bank_capacity > 0 && first >= 0 && count >= 0 && first + count <= bank_capacity, "bad row range");
+  if (h->cfg.precision != OVN_PREC_F16_TC || count == 0) return OVN_OK;
+  if (!h->weights_ready) OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "ovn_bank_prepare: weights not finalised");
+  return tc_bank_prepare(h, d_bank, bank_capacity, first, count, (cudaStream_t)stream);
+}
+
+int ovn_bank_release(ovn_handle* h, const float* d_bank) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  if (h->cfg.precision != OVN_PREC_F16_TC) return OVN_OK;
+  return tc_bank_release(h, d_bank);
 }
 
 // ---- host-buffer entry points ---------------------------------------------------------------------
@@ -508,7 +524,7 @@ int ovn_query_cloud_vs_bank_host(ovn_handle* h, const float* h_points, int64_t n
     if (h_cand_idx) {
       rc = heads_dispatch(h, d_bank, h->d_query_fv, h->d_idx_tmp, nullptr, n_cand, h->d_logit, d_yaw, nullptr, s);
     } else {
-      k_iota<<<(n_cand + 255) / 256, 256, 0, s>>>(h->d_idx_tmp, n_cand);
+      k_iota<<<(n_cand + 255) / 256, 256, 0, s>>>(h->d_idx_tmp, n_cand, 0);
       OVN_LAUNCH_CHECK(h);
       rc = heads_dispatch(h, d_bank, h->d_query_fv, h->d_idx_tmp, nullptr, n_cand, h->d_logit, d_yaw, nullptr, s);
     }

@@ -154,6 +154,8 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query,
                      const int32_t* d_left, const int32_t* d_right, int n, float* d_overlap,
                      int32_t* d_yaw, float* d_corr, cudaStream_t s);
 int tc_pack_weights(ovn_handle* h);
+int tc_bank_prepare(ovn_handle* h, const float* d_bank, int64_t capacity, int64_t first, int64_t count, cudaStream_t s);
+int tc_bank_release(ovn_handle* h, const float* d_bank);
 void tc_free(ovn_handle* h);
 
 }  // namespace ovn

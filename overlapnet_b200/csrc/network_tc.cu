@@ -63,6 +63,11 @@ struct TcState {
   __half* lc = nullptr;         // correlation operands: [max_pairs][3 tiles][2 k-halves][hi,lo][8][128][8]
   __half* rc = nullptr;         // [max_pairs or 1][2 n-halves][hi,lo][16][192][8]
   float* corr_part = nullptr;   // [max_pairs][2][360]
+  // resident bank (ovn_bank_prepare): operand copies of the LEFT volumes, indexed by bank row
+  const float* pb_key = nullptr;
+  int64_t pb_cap = 0, pb_rows = 0;      // capacity / rows [0, pb_rows) prepared
+  __half* pb_l16 = nullptr;             // [cap][360][K4_PITCH]
+  __half* pb_lc = nullptr;              // [cap] x C6_VOL_L_BYTES
   int* d_err = nullptr;
   int64_t rows_pad = 0;
 };
@@ -124,20 +129,21 @@ struct K4Smem {
 // resident: a jb touches just 15 RIGHT rows, which are streamed as a 4 KB double-buffered window;
 // (3) a producer warp's LDS -> ALU -> tcgen05.st -> wait::st -> arrive chain runs at IPC ~0.2, so
 // 16 producer warps in two groups work on alternating steps.
-__global__ void __launch_bounds__(K4_THREADS, 1)
-k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16, int r_per_pair,
-                 const __half* __restrict__ W1p, const float* __restrict__ bias1, __half* __restrict__ o1,
+template <int PROD>   // producer organisation: 1 = 3 groups x 4 warps, full K per thread; 0 = 2 groups x 8 warps, half K per thread
+__global__ void __launch_bounds__(PROD == 1 ? 640 : 768, 1)
+k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_idx, const __half* __restrict__ R16,
+                 int r_per_pair, const __half* __restrict__ W1p, const float* __restrict__ bias1, __half* __restrict__ o1,
                  int64_t rows_pad, int n_pairs, int* __restrict__ err) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   K4Smem& S = *reinterpret_cast<K4Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int s = 0; s < K4_STAGES; ++s) { mbar_init(&S.a_full[s], 4); mbar_init(&S.a_empty[s], 1); }
+    for (int s = 0; s < K4_STAGES; ++s) { mbar_init(&S.a_full[s], PROD == 1 ? 4 : 8); mbar_init(&S.a_empty[s], 1); }
     for (int s = 0; s < K4_BGROUPS; ++s) { mbar_init(&S.b_full[s], 1); mbar_init(&S.b_empty[s], 1); }
     mbar_init(&S.d_full, 1); mbar_init(&S.d_empty, 4);
-    mbar_init(&S.l_full, 1); mbar_init(&S.l_empty, K4_PROD_WARPS);
-    for (int b = 0; b < 2; ++b) { mbar_init(&S.rw_full[b], 1); mbar_init(&S.rw_empty[b], K4_PROD_WARPS); }
+    mbar_init(&S.l_full, 1); mbar_init(&S.l_empty, PROD == 1 ? 12 : 16);
+    for (int b = 0; b < 2; ++b) { mbar_init(&S.rw_full[b], 1); mbar_init(&S.rw_empty[b], PROD == 1 ? 12 : 16); }
     mbar_fence_init();
   }
   if (tid < 64) S.bias[tid] = bias1[tid];
@@ -170,7 +176,7 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
       for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++pi) {
         TC_WAIT(&S.l_empty, (pi & 1) ^ 1, 101);
         mbar_arrive_expect_tx(&S.l_full, VOL_BYTES);
-        bulk_g2s(S.L, L16 + (size_t)p * WF * K4_PITCH, VOL_BYTES, &S.l_full);
+        bulk_g2s(S.L, L16 + (size_t)(l_idx ? l_idx[p] : p) * WF * K4_PITCH, VOL_BYTES, &S.l_full);
         const __half* Rp = R16 + (r_per_pair ? (size_t)p * WF * K4_PITCH : 0);
         for (int jb = 0; jb < NB; ++jb, ++jbit) {
           const uint32_t b = jbit & 1;
@@ -211,11 +217,12 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
               if (sg + 1 < K4_STAGES) ready = mbar_try_wait_addr(a_full0 + (sg + 1) * 8, ph);   // probe ahead
               fence_after_sync();
               if (leader) {
+                // consecutive MMAs go to different accumulator tiles (no back-to-back dependency on one D)
 #pragma unroll
-                for (int t = 0; t < K4_TILES; ++t) {
+                for (int kk = 0; kk < 2; ++kk) {
+                  const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_lo + ((sg * K4_BSLICE + kk * 2048) >> 4));
 #pragma unroll
-                  for (int kk = 0; kk < 2; ++kk) {
-                    const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_lo + ((sg * K4_BSLICE + kk * 2048) >> 4));
+                  for (int t = 0; t < K4_TILES; ++t) {
                     mma_ts(tmem + t * 64, tmem + K4_ACOL0 + sg * K4_STAGE_COLS + t * 16 + kk * 8, bd, idesc,
                            (o | (uint32_t)sg | (uint32_t)kk) != 0);
                   }
@@ -282,11 +289,13 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
     // multiples of 3: dj = g, g+3, ...) into ring slots g, g+3: per synthesised element this costs
     // 1 ALU instruction + ~0.3 of loop / barrier overhead, and a group has three MMA stage-times
     // to hide its LDS -> ALU -> tcgen05.st -> wait::st -> arrive chain.
+    if constexpr (PROD == 1) {
     const int pw = warp - 8, q = pw & 3, grp = pw >> 2;
     const int row0 = q * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + K4_ACOL0;
     const uint32_t a_empty0 = smem_u32(&S.a_empty[0]), a_full0 = smem_u32(&S.a_full[0]);
     uint32_t pi = 0, jbit = 0, n = 0;       // n: steps produced by this group: slot = grp + 3*(n&1), phase = (n>>1)&1
+    bool slot_free = true;                  // result of the probe issued one step ahead (the first two steps find fresh slots)
     for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++pi) {
       TC_WAIT(&S.l_full, pi & 1, 402);
       for (int jb = 0; jb < NB; ++jb, ++jbit) {
@@ -310,7 +319,12 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
           for (int dj = grp; dj < S15; dj += 3, ++n) {
             const uint32_t sg = grp + 3 * (n & 1), ph = (n >> 1) & 1;
             const __half* rrow = &S.Rw[wb][dj * K4_PITCH + ch];
-            if (!mbar_wait_addr(a_empty0 + sg * 8, ph ^ 1, kWaitCycles)) { atomicExch(err, 403); goto done; }
+            if (!slot_free) { if (!mbar_wait_addr(a_empty0 + sg * 8, ph ^ 1, kWaitCycles)) { atomicExch(err, 403); goto done; } }
+            {
+              // probe the slot of this group's NEXT step now; the ~90 clk answer is consumed next iteration
+              const uint32_t n1 = n + 1, sg1 = grp + 3 * (n1 & 1), ph1 = (n1 >> 1) & 1;
+              slot_free = mbar_try_wait_addr(a_empty0 + sg1 * 8, ph1 ^ 1);
+            }
             fence_after_sync();
 #pragma unroll
             for (int hk = 0; hk < 2; ++hk) {          // two 16-channel halves: keeps the live set of r at 8 registers
@@ -341,6 +355,67 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const __half* __restrict__ R16,
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.l_empty);
+    }
+    } else {
+      // 16 warps = 2 groups x (4 TMEM lane quarters x 2 K halves); group g produces steps with step % 2 == g
+      const int pw = warp - 8, q = pw & 3, half = (pw >> 2) & 1, grp = pw >> 3;
+      const int row0 = q * 32 + lane;
+      const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + K4_ACOL0 + half * 8;
+      const uint32_t a_empty0 = smem_u32(&S.a_empty[0]), a_full0 = smem_u32(&S.a_full[0]);
+      uint32_t pi = 0, jbit = 0, sg = grp, ph = 0;
+      for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++pi) {
+        TC_WAIT(&S.l_full, pi & 1, 402);
+        for (int jb = 0; jb < NB; ++jb, ++jbit) {
+          const uint32_t wb = jbit & 1;
+          TC_WAIT(&S.rw_full[wb], (jbit >> 1) & 1, 404);
+#pragma unroll 1
+          for (int cc = 0; cc < 4; ++cc) {
+            const int ch = cc * 32 + half * 16;
+            uint32_t Lr[K4_TILES][8];
+#pragma unroll
+            for (int t = 0; t < K4_TILES; ++t) {
+              const int i = t * 128 + row0;
+              uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+              if (i < WF) {
+                a = *reinterpret_cast<const uint4*>(&S.L[i * K4_PITCH + ch]);
+                b = *reinterpret_cast<const uint4*>(&S.L[i * K4_PITCH + ch + 8]);
+              }
+              Lr[t][0] = a.x; Lr[t][1] = a.y; Lr[t][2] = a.z; Lr[t][3] = a.w;
+              Lr[t][4] = b.x; Lr[t][5] = b.y; Lr[t][6] = b.z; Lr[t][7] = b.w;
+            }
+#pragma unroll 1
+            for (int dj = (grp + cc) & 1; dj < S15; dj += 2) {
+              const __half* rrow = &S.Rw[wb][dj * K4_PITCH + ch];
+              const uint4 ra = *reinterpret_cast<const uint4*>(rrow);
+              const uint4 rb = *reinterpret_cast<const uint4*>(rrow + 8);
+              const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+              if (!mbar_wait_addr(a_empty0 + sg * 8, ph ^ 1, kWaitCycles)) { atomicExch(err, 403); goto done; }
+              fence_after_sync();
+#pragma unroll
+              for (int t = 0; t < K4_TILES; ++t) {
+                uint32_t o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&Lr[t][j]),
+                                            *reinterpret_cast<const __half2*>(&rw[j]));
+                  o[j] = *reinterpret_cast<const uint32_t*>(&d) & 0x7fff7fffu;
+                }
+                tmem_st_x8(lane_addr + sg * K4_STAGE_COLS + t * 16, o);
+              }
+              tmem_st_wait();
+              fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_addr(a_full0 + sg * 8);
+              sg += 2;
+              if (sg >= K4_STAGES) { sg -= K4_STAGES; ph ^= 1; }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S.rw_empty[wb]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.l_empty);
+      }
     }
   }
 done:
@@ -679,7 +754,8 @@ __device__ __forceinline__ int wrap360(int x) {
 }
 
 __global__ void __launch_bounds__(C6_THREADS, 1)
-k_corr_tc(const __half* __restrict__ Lc, const __half* __restrict__ Rc, int r_per_pair, int n_pairs,
+k_corr_tc(const __half* __restrict__ Lc, const int32_t* __restrict__ l_idx, const __half* __restrict__ Rc,
+          int r_per_pair, int n_pairs,
           float* __restrict__ corr_part, int* __restrict__ err) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   C6Smem& S = *reinterpret_cast<C6Smem*>(smem_raw);
@@ -713,11 +789,12 @@ k_corr_tc(const __half* __restrict__ Lc, const __half* __restrict__ Rc, int r_pe
           bulk_g2s(S.R, reinterpret_cast<const uint8_t*>(Rc) + (size_t)p * C6_VOL_R_BYTES + (size_t)h * C6_R_BYTES,
                    C6_R_BYTES, &S.r_full);
         }
+        const int64_t lrow = l_idx ? l_idx[p] : p;
         for (int st = 0; st < 6; ++st, ++it) {
           const uint32_t s = it % C6_STAGES, ph = (it / C6_STAGES) & 1;
           TC_WAIT(&S.empty[s], ph ^ 1, 602);
           mbar_arrive_expect_tx(&S.full[s], C6_STAGE_BYTES);
-          bulk_g2s(S.A[s], reinterpret_cast<const uint8_t*>(Lc) + (size_t)p * C6_VOL_L_BYTES + (size_t)st * C6_STAGE_BYTES,
+          bulk_g2s(S.A[s], reinterpret_cast<const uint8_t*>(Lc) + (size_t)lrow * C6_VOL_L_BYTES + (size_t)st * C6_STAGE_BYTES,
                    C6_STAGE_BYTES, &S.full[s]);
         }
       }
@@ -889,6 +966,8 @@ void tc_free(ovn_handle* h) {
     if (t->leg_plane[l]) cudaFree(t->leg_plane[l]);
     if (t->leg_shift[l]) cudaFree(t->leg_shift[l]);
   }
+  if (t->pb_l16) cudaFree(t->pb_l16);
+  if (t->pb_lc) cudaFree(t->pb_lc);
   if (t->actp[0]) cudaFree(t->actp[0]);
   if (t->actp[1]) cudaFree(t->actp[1]);
   delete t;
@@ -1028,7 +1107,8 @@ int tc_pack_weights(ovn_handle* h) {
   OVN_CUDA(h, cudaMemset(t->d_err, 0, sizeof(int)));
   OVN_CUDA(h, cudaMemset(t->o1, 0, (size_t)120 * t->rows_pad * 8 * sizeof(__half)));
   OVN_CUDA(h, cudaMemset(t->x3, 0, (size_t)16 * t->rows_pad * 8 * sizeof(__half)));
-  OVN_CUDA(h, cudaFuncSetAttribute(k_delta_conv1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem)));
+  OVN_CUDA(h, cudaFuncSetAttribute(k_delta_conv1_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem)));
+  OVN_CUDA(h, cudaFuncSetAttribute(k_delta_conv1_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem)));
 #define OVN_GEMM_ATTR(E, N, T)                                                                                  \
   OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<E, N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                    (int)sizeof(GSmem<N, T>)))
@@ -1112,6 +1192,45 @@ int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cuda
   return OVN_OK;
 }
 
+int tc_bank_release(ovn_handle* h, const float* d_bank) {
+  TcState* t = h->tc;
+  if (!t || (d_bank && t->pb_key != d_bank)) return OVN_OK;
+  OVN_CUDA(h, cudaDeviceSynchronize());
+  if (t->pb_l16) cudaFree(t->pb_l16);
+  if (t->pb_lc) cudaFree(t->pb_lc);
+  t->pb_l16 = t->pb_lc = nullptr;
+  t->pb_key = nullptr;
+  t->pb_cap = t->pb_rows = 0;
+  return OVN_OK;
+}
+
+int tc_bank_prepare(ovn_handle* h, const float* d_bank, int64_t capacity, int64_t first, int64_t count, cudaStream_t s) {
+  TcState* t = h->tc;
+  if (!t) OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "tensor-core weights not packed");
+  if (t->pb_key != d_bank || capacity > t->pb_cap) {
+    if (t->pb_key != nullptr || t->pb_l16) { int rc = tc_bank_release(h, nullptr); if (rc != OVN_OK) return rc; }
+    OVN_CUDA(h, cudaMalloc(&t->pb_l16, (size_t)capacity * WF * K4_PITCH * sizeof(__half)));
+    OVN_CUDA(h, cudaMalloc(&t->pb_lc, (size_t)capacity * C6_VOL_L_BYTES));
+    OVN_CUDA(h, cudaMemsetAsync(t->pb_l16, 0, (size_t)capacity * WF * K4_PITCH * sizeof(__half), s));
+    t->pb_key = d_bank;
+    t->pb_cap = capacity;
+    t->pb_rows = 0;
+    if (first != 0) OVN_SET_ERR(h, OVN_ERR_INVALID_ARG, "ovn_bank_prepare: a new bank must be prepared from row 0");
+  }
+  if (first > t->pb_rows) OVN_SET_ERR(h, OVN_ERR_INVALID_ARG, "ovn_bank_prepare: rows [%lld, %lld) were never prepared",
+                                      (long long)t->pb_rows, (long long)first);
+  const int64_t per = (int64_t)WF * CF / 4, perL = 3 * 2 * 8 * 128;
+  const float* src = d_bank + (size_t)first * WF * CF;
+  k_gather_rows_f16<<<(unsigned)((count * per + 255) / 256), 256, 0, s>>>(src, nullptr, (int)count,
+                                                                         t->pb_l16 + (size_t)first * WF * K4_PITCH);
+  OVN_LAUNCH_CHECK(h);
+  k_pack_corr_L<<<(unsigned)((count * perL + 255) / 256), 256, 0, s>>>(src, nullptr, (int)count,
+                                                                      t->pb_lc + (size_t)first * (C6_VOL_L_BYTES / 2));
+  OVN_LAUNCH_CHECK(h);
+  if (first + count > t->pb_rows) t->pb_rows = first + count;
+  return OVN_OK;
+}
+
 int tc_check_error(ovn_handle* h, cudaStream_t s) {
   int e = 0;
   OVN_CUDA(h, cudaMemcpyAsync(&e, h->tc->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1139,16 +1258,28 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query, c
     const int np = (n - p0 < maxp) ? n - p0 : maxp;
     const int32_t* left = d_left + p0;
     const int32_t* right = d_right ? d_right + p0 : nullptr;
-    k_gather_rows_f16<<<(unsigned)((np * per + 255) / 256), 256, 0, s>>>(d_bank, left, np, t->l16);
-    OVN_LAUNCH_CHECK(h);
+    // resident bank: the LEFT operand copies already exist, the kernels index them through `left`
+    const bool resident = (t->pb_key == d_bank) && t->pb_rows > 0;
+    const __half* l16 = resident ? t->pb_l16 : t->l16;
+    const __half* lc = resident ? t->pb_lc : t->lc;
+    const int32_t* lidx = resident ? left : nullptr;
+    if (!resident) {
+      k_gather_rows_f16<<<(unsigned)((np * per + 255) / 256), 256, 0, s>>>(d_bank, left, np, t->l16);
+      OVN_LAUNCH_CHECK(h);
+    }
     if (!d_query) {
       k_gather_rows_f16<<<(unsigned)((np * per + 255) / 256), 256, 0, s>>>(d_bank, right, np, t->r16);
       OVN_LAUNCH_CHECK(h);
     }
     const int grid4 = np < h->sm_count ? np : h->sm_count;
+    static const int prod = getenv("OVN_K4_PROD") ? atoi(getenv("OVN_K4_PROD")) : 1;
     prof_mark(h, PROF_DELTA, s);
-    k_delta_conv1_tc<<<grid4, K4_THREADS, sizeof(K4Smem), s>>>(t->l16, t->r16, d_query ? 0 : 1, t->w1p,
-                                                               h->d_b[base + 0], t->o1, t->rows_pad, np, t->d_err);
+    if (prod == 1)
+      k_delta_conv1_tc<1><<<grid4, 640, sizeof(K4Smem), s>>>(l16, lidx, t->r16, d_query ? 0 : 1, t->w1p, h->d_b[base + 0],
+                                                             t->o1, t->rows_pad, np, t->d_err);
+    else
+      k_delta_conv1_tc<0><<<grid4, 768, sizeof(K4Smem), s>>>(l16, lidx, t->r16, d_query ? 0 : 1, t->w1p, h->d_b[base + 0],
+                                                             t->o1, t->rows_pad, np, t->d_err);
     prof_mark(h, PROF_DELTA, s);
     OVN_LAUNCH_CHECK(h);
     const int64_t M = (int64_t)np * PAIR_ROWS;
@@ -1177,8 +1308,10 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query, c
     // correlation head (tensor cores, hi/lo split operands)
     {
       const int64_t perL = 3 * 2 * 8 * 128, perR = 2 * 16 * 192;
-      k_pack_corr_L<<<(unsigned)((np * perL + 255) / 256), 256, 0, s>>>(d_bank, left, np, t->lc);
-      OVN_LAUNCH_CHECK(h);
+      if (!resident) {
+        k_pack_corr_L<<<(unsigned)((np * perL + 255) / 256), 256, 0, s>>>(d_bank, left, np, t->lc);
+        OVN_LAUNCH_CHECK(h);
+      }
       if (d_query) {
         if (p0 == 0) {
           k_pack_corr_R<<<(unsigned)((perR + 255) / 256), 256, 0, s>>>(d_query, nullptr, 1, t->rc);
@@ -1192,7 +1325,7 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query, c
       if (g6 > np) g6 = np;
       if (g6 < 1) g6 = 1;
       prof_mark(h, PROF_CORR, s);
-      k_corr_tc<<<2 * g6, C6_THREADS, sizeof(C6Smem), s>>>(t->lc, t->rc, d_query ? 0 : 1, np, t->corr_part, t->d_err);
+      k_corr_tc<<<2 * g6, C6_THREADS, sizeof(C6Smem), s>>>(lc, lidx, t->rc, d_query ? 0 : 1, np, t->corr_part, t->d_err);
       prof_mark(h, PROF_CORR, s);
       OVN_LAUNCH_CHECK(h);
       k_corr_finalize<<<np, 384, 0, s>>>(t->corr_part, d_corr ? d_corr + (int64_t)p0 * WF : nullptr, d_yaw + p0);

@@ -217,6 +217,16 @@ class Engine:
                                        _ptr(yaw), _ptr(corr), self._stream()), 'ovn_heads_1vsN')
     return ov, yaw, corr
 
+  def bank_prepare(self, bank, first=0, count=None):
+    """Keep the tensor-core operand copies of bank rows [first, first+count) resident: later heads
+    calls on this same tensor skip the per-call conversion (ovn_bank_prepare)."""
+    count = int(bank.shape[0]) - first if count is None else int(count)
+    check(self._h, lib().ovn_bank_prepare(self._h, _ptr(bank), int(bank.shape[0]), int(first), count, self._stream()),
+          'ovn_bank_prepare')
+
+  def bank_release(self, bank=None):
+    check(self._h, lib().ovn_bank_release(self._h, _ptr(bank)), 'ovn_bank_release')
+
   # ---- host-buffer entry points (synchronous) ------------------------------------------------
   def encode_clouds_host(self, clouds):
     offs = np.zeros(len(clouds) + 1, np.int64)

@@ -125,6 +125,8 @@ class Infer():
   def _set_bank(self, fv):
     self._bank = fv.contiguous()
     self._bank_n = int(fv.shape[0])
+    if self._bank_n:
+      self._engine.bank_prepare(self._bank, 0, self._bank_n)      # resident tensor-core operand copies
 
   def _append_bank(self, fv):
     n = int(fv.shape[0])
@@ -133,7 +135,10 @@ class Infer():
       nb = torch.empty((cap, self.network_output_size, FEAT_C), dtype=torch.float32, device=self._engine.device)
       nb[:self._bank_n] = self._bank[:self._bank_n]
       self._bank = nb
+      if self._bank_n:
+        self._engine.bank_prepare(self._bank, 0, self._bank_n)    # new storage: rebuild the resident copies
     self._bank[self._bank_n:self._bank_n + n] = fv
+    self._engine.bank_prepare(self._bank, self._bank_n, n)
     self._bank_n += n
 
   # ---- keras-model shims ---------------------------------------------------------------------

@@ -86,6 +86,14 @@ def test_heads_match_oracle(setup, prec):
   assert np.array_equal(ov1.cpu().numpy(), ov[:6]) and np.array_equal(yaw1.cpu().numpy(), yaw[:6])
   ov2, yaw2, _ = eng.heads_1vsN(bank, bank[5], n_cand=6)
   assert np.array_equal(ov2.cpu().numpy(), ov[:6]) and np.array_equal(yaw2.cpu().numpy(), yaw[:6])
+  # resident bank (ovn_bank_prepare): identical results without the per-call operand conversion
+  eng.bank_prepare(bank)
+  ov3, yaw3, corr3 = eng.heads(bank, torch.from_numpy(left), torch.from_numpy(right), want_corr=True)
+  assert np.array_equal(ov3.cpu().numpy(), ov) and np.array_equal(yaw3.cpu().numpy(), yaw)
+  assert np.array_equal(corr3.cpu().numpy(), corr)
+  ov4, yaw4, _ = eng.heads_1vsN(bank, bank[5], n_cand=6)
+  assert np.array_equal(ov4.cpu().numpy(), ov[:6]) and np.array_equal(yaw4.cpu().numpy(), yaw[:6])
+  eng.bank_release(bank)
   eng.close()
 
 

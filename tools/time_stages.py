@@ -24,7 +24,11 @@ eng.load_weights(N.glorot_weights(4, MODEL, seed=0))
 clouds = [synth.kitti_like_cloud(s) for s in range(64)]
 batch = eng.upload_clouds(clouds)
 npts = sum(c.shape[0] for c in clouds)
+eng.profile_enable(True)
 t = timeit(lambda: eng.preprocess(batch))
+for k in ('project_scatter','project_gather'):
+  ms, n = eng.profile_read(k); print('  %s: %.1f us per launch (%d launches)' % (k, ms / max(n,1) * 1e3, n))
+eng.profile_enable(False)
 print('preprocess 64 scans: %.3f ms  -> %.1f Mpts/s, %.1f GB/s algorithmic' % (t, npts / t / 1e3, (npts * 16 + 64 * 57600 * 16) / t / 1e6))
 t = timeit(lambda: eng.project(batch))
 print('project(all outputs incl idx) 64 scans: %.3f ms -> %.1f Mpts/s' % (t, npts / t / 1e3))
