@@ -504,21 +504,22 @@ k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
   const uint32_t tmem = S.tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t s = 0, ph = 0;
-      for (int sl = 0; sl < g.n_slabs; ++sl) {
-        TC_WAIT(&S.empty[s], ph ^ 1, 501);
-        mbar_arrive_expect_tx(&S.full[s], G_A_BYTES + B_BYTES);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int2 ps = S.tab[sl * 4 + j];
-          const int64_t plane = in_base + ps.x;
-          const int64_t r = row0 + ps.y;
-          bulk_g2s(S.A[s] + j * (G_ROWS * 16), g.A + ((size_t)plane * g.a_pitch + r) * 8, G_ROWS * 16, &S.full[s]);
-        }
+    // the whole warp walks the ring; lanes 0..3 each issue one activation-plane copy and lane 4 the
+    // weight slab, so a slab costs one bulk-copy issue latency instead of five in a row
+    uint32_t s = 0, ph = 0;
+    for (int sl = 0; sl < g.n_slabs; ++sl) {
+      TC_WAIT(&S.empty[s], ph ^ 1, 501);
+      if (lane == 0) mbar_arrive_expect_tx(&S.full[s], G_A_BYTES + B_BYTES);
+      __syncwarp();
+      if (lane < 4) {
+        const int2 ps = S.tab[sl * 4 + lane];
+        const int64_t plane = in_base + ps.x;
+        const int64_t r = row0 + ps.y;
+        bulk_g2s(S.A[s] + lane * (G_ROWS * 16), g.A + ((size_t)plane * g.a_pitch + r) * 8, G_ROWS * 16, &S.full[s]);
+      } else if (lane == 4) {
         bulk_g2s(S.B[s], g.Bp + ((size_t)nh * g.n_slabs + sl) * (B_BYTES / 2), B_BYTES, &S.full[s]);
-        if (++s == G_STAGES) { s = 0; ph ^= 1; }
       }
+      if (++s == G_STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // warp-uniform loop, one elected lane issues; descriptors advance by 32-bit adds
@@ -649,6 +650,134 @@ done:
   fence_before_sync();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_conv3_resident_tc -- c_conv3 (3x3, 128 -> 256, ReLU) + Flatten + Dense partial sums.
+// The streamed GEMM re-reads the activation tile for each of the 9 taps and both N halves
+// (3.6 GB of L2 traffic per 1101 pairs: L2-bound).  Here the 16 activation planes of a 512-row tile
+// (+64 halo rows) are loaded ONCE (144 KB) and the 3x3 window is applied by the UMMA descriptor
+// itself: tap (dy, dx) is a start-address offset of (dy*24 + dx) rows in the SWIZZLE_NONE layout
+// (16-byte rows at uniform pitch -- probe mode 2).  Only the weights (8 KB per slab) are streamed.
+// ------------------------------------------------------------------------------------------------
+constexpr int C3_ROWS = 512, C3_WIN = 576, C3_PLANES = 16, C3_SLABS = 36, C3_STAGES = 4;
+constexpr int C3_PLANE_BYTES = C3_WIN * 16;             // 9216
+constexpr int C3_B_BYTES = 4 * 128 * 16;                // 8192
+
+struct C3Smem {
+  uint8_t A[C3_PLANES][C3_PLANE_BYTES];
+  uint8_t B[C3_STAGES][C3_B_BYTES];
+  float bias[128];
+  uint64_t a_full, full[C3_STAGES], empty[C3_STAGES], d_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+k_conv3_resident_tc(const __half* __restrict__ X3, int64_t a_pitch, const __half* __restrict__ Bp,
+                    const float* __restrict__ bias, int64_t M, const float* __restrict__ wd, float* __restrict__ partial,
+                    int* __restrict__ err) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  C3Smem& S = *reinterpret_cast<C3Smem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * C3_ROWS;
+  const int nh = blockIdx.z;
+  if (tid == 0) {
+    mbar_init(&S.a_full, 1);
+    for (int s = 0; s < C3_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    mbar_init(&S.d_full, 1);
+    mbar_fence_init();
+  }
+  if (tid < 128) S.bias[tid] = bias[nh * 128 + tid];
+  if (warp == 2) tmem_alloc(&S.tmem_base, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&S.a_full, C3_PLANES * C3_PLANE_BYTES);
+      for (int pl = 0; pl < C3_PLANES; ++pl)
+        bulk_g2s(S.A[pl], X3 + ((size_t)pl * a_pitch + row0) * 8, C3_PLANE_BYTES, &S.a_full);
+      uint32_t s = 0, ph = 0;
+      for (int sl = 0; sl < C3_SLABS; ++sl) {
+        TC_WAIT(&S.empty[s], ph ^ 1, 701);
+        mbar_arrive_expect_tx(&S.full[s], C3_B_BYTES);
+        bulk_g2s(S.B[s], Bp + ((size_t)nh * C3_SLABS + sl) * (C3_B_BYTES / 2), C3_B_BYTES, &S.full[s]);
+        if (++s == C3_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_f16(128, 128);
+    const bool leader = elect_one() != 0;
+    const uint64_t ad0 = make_desc_kmajor_noswizzle(smem_u32(S.A[0]), C3_PLANE_BYTES, 128);
+    const uint64_t bd0 = make_desc_kmajor_noswizzle(smem_u32(S.B[0]), 128 * 16, 128);
+    const uint32_t ad_hi = (uint32_t)(ad0 >> 32), ad_lo = (uint32_t)ad0;
+    const uint32_t bd_hi = (uint32_t)(bd0 >> 32), bd_lo = (uint32_t)bd0;
+    TC_WAIT(&S.a_full, 0, 702);
+    uint32_t sg = 0, ph = 0;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const uint32_t shift = (tap / 3) * NB + (tap % 3);                // rows
+#pragma unroll 1
+      for (int gq = 0; gq < 4; ++gq) {                                  // slab = (tap, 32-channel group)
+        TC_WAIT(&S.full[sg], ph, 703);
+        fence_after_sync();
+        if (leader) {
+          const uint32_t b_off = (sg * C3_B_BYTES) >> 4;
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(bd_lo + b_off + ((kk * 2 * (128 * 16)) >> 4));
+            const uint32_t a_k = ad_lo + (((gq * 4 + kk * 2) * C3_PLANE_BYTES + shift * 16) >> 4);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const uint64_t ad = ((uint64_t)ad_hi << 32) | (uint64_t)(a_k + ((t * 128 * 16) >> 4));
+              mma_ss(tmem + t * 128, ad, bd, idesc, (tap | gq | kk) != 0);
+            }
+          }
+          commit(&S.empty[sg]);
+        }
+        __syncwarp();
+        if (++sg == C3_STAGES) { sg = 0; ph ^= 1; }
+      }
+    }
+    if (leader) commit(&S.d_full);
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    TC_WAIT(&S.d_full, 0, 704);
+    fence_after_sync();
+#pragma unroll 1
+    for (int t = 0; t < 4; ++t) {
+      const int64_t r = row0 + t * 128 + q * 32 + lane;
+      const int rem = (int)(r % PAIR_ROWS);
+      const int yy = rem / NB, xx = rem - yy * NB;
+      const bool valid = (r < M) && (yy < NB - 2) && (xx < NB - 2);
+      const float* wrow = wd + ((size_t)(valid ? (yy * (NB - 2) + xx) : 0) * 256 + nh * 128);
+      float acc = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * 128 + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + c0) + j4);
+            acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 0]) + S.bias[c0 + j4 * 4 + 0], 0.f), w.x, acc);
+            acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 1]) + S.bias[c0 + j4 * 4 + 1], 0.f), w.y, acc);
+            acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 2]) + S.bias[c0 + j4 * 4 + 2], 0.f), w.z, acc);
+            acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 3]) + S.bias[c0 + j4 * 4 + 3], 0.f), w.w, acc);
+          }
+        }
+      }
+      if (r < M) partial[r * 2 + nh] = valid ? acc : 0.f;
+    }
+  }
+done:
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1113,6 +1242,7 @@ int tc_pack_weights(ovn_handle* h) {
   OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<E, N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                    (int)sizeof(GSmem<N, T>)))
   OVN_GEMM_ATTR(1, 128, 4); OVN_GEMM_ATTR(2, 128, 4);
+  OVN_CUDA(h, cudaFuncSetAttribute(k_conv3_resident_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(C3Smem)));
   OVN_GEMM_ATTR(4, 64, 4); OVN_GEMM_ATTR(4, 128, 4); OVN_GEMM_ATTR(3, 128, 4);
   OVN_GEMM_ATTR(4, 64, 1); OVN_GEMM_ATTR(3, 64, 1);
 #undef OVN_GEMM_ATTR
@@ -1300,7 +1430,8 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query, c
     a3.wd = h->d_w[base + 3]; a3.partial = t->partial; a3.grid_w = NB; a3.valid_w = NB - 2; a3.valid_h = NB - 2;
     a3.n_total = 256;
     prof_mark(h, PROF_CONV3, s);
-    k_gemm_stream_tc<2, 128, 4><<<dim3(gx, 1, 2), G_THREADS, sizeof(GSmem<128, 4>), s>>>(a3, t->d_err);
+    k_conv3_resident_tc<<<dim3(gx, 1, 2), G_THREADS, sizeof(C3Smem), s>>>(t->x3, t->rows_pad, t->w3p, h->d_b[base + 2], M,
+                                                                        h->d_w[base + 3], t->partial, t->d_err);
     prof_mark(h, PROF_CONV3, s);
     OVN_LAUNCH_CHECK(h);
     k_dense_finalize<<<np, 256, 0, s>>>(t->partial, h->d_b[base + 3], PAIR_ROWS, d_overlap + p0);
