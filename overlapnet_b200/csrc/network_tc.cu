@@ -49,7 +49,8 @@ struct TcState {
   int* slab3_plane = nullptr; int* slab3_shift = nullptr;
   // tensor-core leg (layers 2..): packed weights + copy tables per layer, ping-pong activation planes
   __half* wleg[kMaxLegLayers] = {};      // [1][n_slabs][4][NT][8]   (throughput mode)
-  __half* wleg64[kMaxLegLayers] = {};    // [cout/64][n_slabs][4][64][8] (latency mode)
+  __half* wleg64[kMaxLegLayers] = {};    // [cout/64][n_slabs][4][64][8] (streamed, 64-wide)
+  __half* wres[kMaxLegLayers] = {};      // [cout/64][kh*kw*3][C_in/8][64][8] (latency mode, resident activations)
   int* leg_plane[kMaxLegLayers] = {};
   int* leg_shift[kMaxLegLayers] = {};
   int leg_slabs[kMaxLegLayers] = {};
@@ -781,6 +782,169 @@ done:
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_leg_resident_tc -- one leg layer in latency mode (single query scan).
+// Measured (profiles/r1_ncu_summary): the streamed GEMM needs 5 small bulk copies per K slab and a
+// CTA cannot get more than ~1 bulk copy per ~150 clk through, so a 108-slab layer took 45 us at 9 %
+// tensor activity.  Here the activation window of the CTA's 128 output pixels (kh input rows x
+// [hi, lo] x C_in/8 planes x (128 + kw - 1) pixels, <= 108 KB) is loaded once and every (dh, dw) tap
+// is a descriptor offset into it; only the weights move: one copy per (tap, split term) of
+// C_in x 64 x 2 B.  Three-term hi/lo split product as in the streamed leg (fp32-grade accuracy).
+// ------------------------------------------------------------------------------------------------
+constexpr int LR_WIN = 144;                       // 128 + max(kw) - 1 = 142, rounded to a multiple of 8
+constexpr int LR_A_MAX = 48 * LR_WIN * 16;        // 110 592 B (s_conv3a: 3 rows x 2 x 8 planes)
+constexpr int LR_B_MAX = 16 * 64 * 16;            // 16 384 B  (C_in = 128)
+constexpr int LR_STAGES = 5;
+
+struct LRSmem {
+  uint8_t A[LR_A_MAX];
+  uint8_t B[LR_STAGES][LR_B_MAX];
+  float bias[64];
+  uint64_t a_full, full[LR_STAGES], empty[LR_STAGES], d_full;
+  uint32_t tmem_base;
+};
+
+struct LegArgs {
+  const __half* A; int64_t a_pitch;
+  int runs_per_img, in_img_planes, in_run_planes;
+  int kh, kw, c8in;
+  const __half* Bp;           // [cout/64][kh*kw*3][c8in][64][8]
+  const float* bias; int n_valid;
+  int64_t M;                  // output pixels per run
+  __half* out_planes; int64_t out_pitch; int out_run_planes;   // EPI 4
+  float* out_f32;                                               // EPI 3
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(G_THREADS, 1)
+k_leg_resident_tc(LegArgs g, int* __restrict__ err) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  LRSmem& S = *reinterpret_cast<LRSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * 128;
+  const int y = blockIdx.y, nh = blockIdx.z;
+  const int64_t in_base = (int64_t)(y / g.runs_per_img) * g.in_img_planes + (int64_t)(y % g.runs_per_img) * g.in_run_planes;
+  const int n_planes = g.kh * 2 * g.c8in;
+  const int n_slabs = g.kh * g.kw * 3;
+  const uint32_t b_bytes = (uint32_t)g.c8in * 64 * 16;
+
+  if (tid == 0) {
+    mbar_init(&S.a_full, 1);
+    for (int s = 0; s < LR_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    mbar_init(&S.d_full, 1);
+    mbar_fence_init();
+  }
+  if (tid < 64) S.bias[tid] = (nh * 64 + tid < g.n_valid) ? g.bias[nh * 64 + tid] : 0.f;
+  if (warp == 2) tmem_alloc(&S.tmem_base, 64);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp == 0) {
+    // activation window: one copy per plane, issued by the lanes in parallel
+    if (lane == 0) mbar_arrive_expect_tx(&S.a_full, (uint32_t)n_planes * LR_WIN * 16);
+    __syncwarp();
+    for (int pl = lane; pl < n_planes; pl += 32)
+      bulk_g2s(S.A + (size_t)pl * LR_WIN * 16, g.A + ((size_t)(in_base + pl) * g.a_pitch + row0) * 8, LR_WIN * 16, &S.a_full);
+    uint32_t s = 0, ph = 0;
+    for (int sl = 0; sl < n_slabs; ++sl) {
+      TC_WAIT(&S.empty[s], ph ^ 1, 801);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&S.full[s], b_bytes);
+        bulk_g2s(S.B[s], g.Bp + ((size_t)nh * n_slabs + sl) * (b_bytes / 2), b_bytes, &S.full[s]);
+      }
+      __syncwarp();
+      if (++s == LR_STAGES) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_f16(128, 64);
+    const bool leader = elect_one() != 0;
+    const uint64_t ad0 = make_desc_kmajor_noswizzle(smem_u32(S.A), LR_WIN * 16, 128);
+    const uint64_t bd0 = make_desc_kmajor_noswizzle(smem_u32(S.B[0]), 64 * 16, 128);
+    const uint32_t ad_hi = (uint32_t)(ad0 >> 32), ad_lo = (uint32_t)ad0;
+    const uint32_t bd_hi = (uint32_t)(bd0 >> 32), bd_lo = (uint32_t)bd0;
+    TC_WAIT(&S.a_full, 0, 802);
+    uint32_t sg = 0, ph = 0, first = 1;
+    for (int dh = 0; dh < g.kh; ++dh) {
+      for (int dw = 0; dw < g.kw; ++dw) {
+#pragma unroll 1
+        for (int term = 0; term < 3; ++term) {            // x*w ~= xh*wh + xl*wh + xh*wl
+          TC_WAIT(&S.full[sg], ph, 803);
+          fence_after_sync();
+          if (leader) {
+            const uint32_t kind = (term == 1) ? 1u : 0u;
+            const uint32_t a_k = ad_lo + ((((dh * 2 + kind) * g.c8in) * (LR_WIN * 16) + dw * 16) >> 4);
+            const uint32_t b_k = bd_lo + ((sg * LR_B_MAX) >> 4);
+            for (int c16 = 0; c16 < g.c8in / 2; ++c16) {
+              const uint64_t ad = ((uint64_t)ad_hi << 32) | (uint64_t)(a_k + ((c16 * 2 * (LR_WIN * 16)) >> 4));
+              const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_k + ((c16 * 2 * (64 * 16)) >> 4));
+              mma_ss(tmem, ad, bd, idesc, first ? 0u : 1u);
+              first = 0;
+            }
+            commit(&S.empty[sg]);
+          }
+          first = 0;
+          __syncwarp();
+          if (++sg == LR_STAGES) { sg = 0; ph ^= 1; }
+        }
+      }
+    }
+    if (leader) commit(&S.d_full);
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    TC_WAIT(&S.d_full, 0, 804);
+    fence_after_sync();
+    const int64_t r = row0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      if (r < g.M && nh * 64 + c0 < g.n_valid) {
+        if (EPI == 4) {
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            uint32_t phh[4], pll[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n = c0 + h8 * 8 + 2 * j;
+              const float a = fmaxf(__uint_as_float(v[h8 * 8 + 2 * j]) + S.bias[n], 0.f);
+              const float b = fmaxf(__uint_as_float(v[h8 * 8 + 2 * j + 1]) + S.bias[n + 1], 0.f);
+              const __half2 hi = __floats2half2_rn(a, b);
+              const float2 hf = __half22float2(hi);
+              const __half2 lo = __floats2half2_rn(a - hf.x, b - hf.y);
+              phh[j] = *reinterpret_cast<const uint32_t*>(&hi);
+              pll[j] = *reinterpret_cast<const uint32_t*>(&lo);
+            }
+            const int c8 = nh * 8 + (c0 >> 3) + h8;
+            const int64_t plane = (int64_t)y * g.out_run_planes + c8;
+            *reinterpret_cast<uint4*>(g.out_planes + ((size_t)plane * g.out_pitch + r) * 8) = make_uint4(phh[0], phh[1], phh[2], phh[3]);
+            *reinterpret_cast<uint4*>(g.out_planes + ((size_t)(plane + g.out_run_planes / 2) * g.out_pitch + r) * 8) =
+                make_uint4(pll[0], pll[1], pll[2], pll[3]);
+          }
+        } else {
+          float* dst = g.out_f32 + ((size_t)y * g.M + r) * g.n_valid + nh * 64 + c0;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            float4 o;
+            o.x = fmaxf(__uint_as_float(v[j4 * 4 + 0]) + S.bias[c0 + j4 * 4 + 0], 0.f);
+            o.y = fmaxf(__uint_as_float(v[j4 * 4 + 1]) + S.bias[c0 + j4 * 4 + 1], 0.f);
+            o.z = fmaxf(__uint_as_float(v[j4 * 4 + 2]) + S.bias[c0 + j4 * 4 + 2], 0.f);
+            o.w = fmaxf(__uint_as_float(v[j4 * 4 + 3]) + S.bias[c0 + j4 * 4 + 3], 0.f);
+            reinterpret_cast<float4*>(dst)[j4] = o;
+          }
+        }
+      }
+    }
+  }
+done:
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 64);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Correlation (yaw) head on tensor cores.
 //   G = L R^T (360 x 360, K = 128), corr[k] = sum_j G[(k + j + 180) mod 360, j]
 //   (RangePadding2D.py:34 + NormalizedCorrelation2D.py:96-109), yaw = 180 - argmax (infer.py:158).
@@ -1092,6 +1256,7 @@ void tc_free(ovn_handle* h) {
   for (int l = 0; l < kMaxLegLayers; ++l) {
     if (t->wleg[l]) cudaFree(t->wleg[l]);
     if (t->wleg64[l]) cudaFree(t->wleg64[l]);
+    if (t->wres[l]) cudaFree(t->wres[l]);
     if (t->leg_plane[l]) cudaFree(t->leg_plane[l]);
     if (t->leg_shift[l]) cudaFree(t->leg_shift[l]);
   }
@@ -1211,6 +1376,26 @@ int tc_pack_weights(ovn_handle* h) {
     int rc2;
     if ((rc2 = upload_vec(h, &t->wleg[l], bp)) != OVN_OK) return rc2;
     if ((rc2 = upload_vec(h, &t->wleg64[l], bp64)) != OVN_OK) return rc2;
+    {
+      // resident-activation layout: slab = (dh, dw, term), rows = all C_in/8 chunks, 64 output channels
+      const int nsl = L.kh * L.kw * 3;
+      std::vector<__half> br((size_t)nz * nsl * c8in * 64 * 8, __float2half(0.f));
+      for (int z = 0; z < nz; ++z)
+        for (int dh = 0; dh < L.kh; ++dh)
+          for (int dw = 0; dw < L.kw; ++dw)
+            for (int term = 0; term < 3; ++term) {
+              const int sl = (dh * L.kw + dw) * 3 + term;
+              for (int c8 = 0; c8 < c8in; ++c8)
+                for (int n = 0; n < 64 && z * 64 + n < L.cout; ++n)
+                  for (int k = 0; k < 8; ++k) {
+                    const float wf = w.kernel[(((size_t)dh * L.kw + dw) * L.cin + c8 * 8 + k) * L.cout + z * 64 + n];
+                    const __half wh = __float2half(wf);
+                    const __half wl = __float2half(wf - __half2float(wh));
+                    br[((((size_t)z * nsl + sl) * c8in + c8) * 64 + n) * 8 + k] = (term == 2) ? wl : wh;
+                  }
+            }
+      if ((rc2 = upload_vec(h, &t->wres[l], br)) != OVN_OK) return rc2;
+    }
     if ((rc2 = upload_vec(h, &t->leg_plane[l], cp)) != OVN_OK) return rc2;
     if ((rc2 = upload_vec(h, &t->leg_shift[l], cs)) != OVN_OK) return rc2;
   }
@@ -1245,6 +1430,8 @@ int tc_pack_weights(ovn_handle* h) {
   OVN_CUDA(h, cudaFuncSetAttribute(k_conv3_resident_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(C3Smem)));
   OVN_GEMM_ATTR(4, 64, 4); OVN_GEMM_ATTR(4, 128, 4); OVN_GEMM_ATTR(3, 128, 4);
   OVN_GEMM_ATTR(4, 64, 1); OVN_GEMM_ATTR(3, 64, 1);
+  OVN_CUDA(h, cudaFuncSetAttribute(k_leg_resident_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LRSmem)));
+  OVN_CUDA(h, cudaFuncSetAttribute(k_leg_resident_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LRSmem)));
 #undef OVN_GEMM_ATTR
   return OVN_OK;
 }
@@ -1306,9 +1493,13 @@ int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cuda
     if (last && (L.cout != 128 || L.h_out != 1)) OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "tensor-core leg: unexpected last layer");
     if (latency) {
       const dim3 grid((unsigned)((L.w_out + 127) / 128), (unsigned)(n * L.h_out), (unsigned)((L.cout + 63) / 64));
-      a.Bp = t->wleg64[l];
-      if (last) k_gemm_stream_tc<3, 64, 1><<<grid, G_THREADS, sizeof(GSmem<64, 1>), s>>>(a, t->d_err);
-      else k_gemm_stream_tc<4, 64, 1><<<grid, G_THREADS, sizeof(GSmem<64, 1>), s>>>(a, t->d_err);
+      LegArgs la = {};
+      la.A = a.A; la.a_pitch = a.a_pitch; la.runs_per_img = a.runs_per_img; la.in_img_planes = a.in_img_planes;
+      la.in_run_planes = a.in_run_planes; la.kh = L.kh; la.kw = L.kw; la.c8in = L.cin / 8; la.Bp = t->wres[l];
+      la.bias = h->d_b[l]; la.n_valid = L.cout; la.M = L.w_out; la.out_planes = a.out_planes; la.out_pitch = a.out_pitch;
+      la.out_run_planes = a.out_run_planes; la.out_f32 = d_fv;
+      if (last) k_leg_resident_tc<3><<<grid, G_THREADS, sizeof(LRSmem), s>>>(la, t->d_err);
+      else k_leg_resident_tc<4><<<grid, G_THREADS, sizeof(LRSmem), s>>>(la, t->d_err);
     } else {
       const dim3 grid(1, (unsigned)(n * L.h_out), 1);
       if (last) k_gemm_stream_tc<3, 128, 4><<<grid, G_THREADS, sizeof(GSmem<128, 4>), s>>>(a, t->d_err);
