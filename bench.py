@@ -68,12 +68,17 @@ class ClockSampler(threading.Thread):
     super().__init__(daemon=True)
     self.index, self.rows, self.proc = index, [], None
 
+  def wait_first_sample(self, timeout=5.0):
+    t0 = time.time()
+    while not self.rows and time.time() - t0 < timeout:
+      time.sleep(0.02)
+
   def run(self):
     q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
     try:
       self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
-                                    '--format=csv,noheader,nounits', '-lms', '100'],
+                                    '--format=csv,noheader,nounits', '-lms', '20'],
                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       for line in self.proc.stdout:
         self.rows.append([x.strip() for x in line.split(',')])
@@ -256,7 +261,7 @@ def main():
   sampler = ClockSampler(local) if rank == 0 else None
   if sampler:
     sampler.start()
-    time.sleep(0.3)
+    sampler.wait_first_sample()
   eng.profile_enable(True)
   for k in ('delta_conv1', 'conv2', 'conv3', 'corr', 'leg', 'project_scatter', 'project_gather'):
     eng.profile_read(k)
@@ -286,6 +291,12 @@ def main():
     proj_ms = (prof['project_scatter'][0] + prof['project_gather'][0]) / max(prof['project_scatter'][1], 1)
     npts = int(q_host[0].shape[0])
     cpu_val, cpu_dt = cpu_pairs_per_s(w, args.cpu_pairs, threads=os.cpu_count())
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'r1_delta_traffic.json')
+    if os.path.exists(tp) and args.precision == 'f16_tc':
+      with open(tp) as f:
+        tj = json.load(f)
+      traffic = (tj['dram_bytes_read'] + tj['dram_bytes_write']) * N_CAND / tj['pairs_per_launch']
     line = {
         'metric': METRIC, 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -301,7 +312,9 @@ def main():
                 'd2h_bytes_per_step': int(N_CAND * 8 * world)},
         'roofline': {'kernel': 'k_delta_conv1_tc' if args.precision == 'f16_tc' else 'k_simt_gemm<DeltaOperand>',
                      'bound': 'tensor', 'achieved': ach, 'peak': tflops_peak, 'unit': 'TFLOP/s',
-                     'frac': (ach / tflops_peak) if ach else None, 'traffic': None, 'peak_source': peak_src,
+                     'frac': (ach / tflops_peak) if ach else None, 'traffic': traffic,
+                     'traffic_note': 'DRAM bytes per launch from the committed ncu capture (profiles/r1_ncu_summary.txt); algorithmic bytes 1.32e9',
+                     'peak_source': peak_src,
                      'flop_per_launch': N_CAND * FLOP_DELTA_CONV1, 'avg_launch_ms': k_ms / max(k_n, 1),
                      'share_of_step': shares},
         'range_proj': {'mpts_per_s': npts / (proj_ms * 1e-3) / 1e6 if proj_ms else None, 'scans_per_launch': 1,

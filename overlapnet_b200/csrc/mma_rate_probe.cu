@@ -7,7 +7,7 @@
 #include "umma.cuh"
 using namespace umma;
 
-__global__ void __launch_bounds__(512, 1) rate_kernel(long long* out, int n_mma, int N, int ts, int st_warps, int per_commit) {
+__global__ void __launch_bounds__(512, 1) rate_kernel(long long* out, int n_mma, int N, int ts, int st_warps, int per_commit, int sw) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t s_tmem;
@@ -20,8 +20,8 @@ __global__ void __launch_bounds__(512, 1) rate_kernel(long long* out, int n_mma,
   const uint32_t tmem = s_tmem;
   if (warp == 1) {
     const uint32_t idesc = make_idesc_f16(128, N);
-    const uint64_t ad = make_desc_kmajor_noswizzle(smem_u32(smem), 128 * 16, 128);
-    const uint64_t bd = make_desc_kmajor_noswizzle(smem_u32(smem + 16384), N * 16, 128);
+    const uint64_t ad = sw ? make_desc_kmajor_sw128(smem_u32(smem), 0) : make_desc_kmajor_noswizzle(smem_u32(smem), 128 * 16, 128);
+    const uint64_t bd = sw ? make_desc_kmajor_sw128(smem_u32(smem + 16384), 0) : make_desc_kmajor_noswizzle(smem_u32(smem + 16384), N * 16, 128);
     const bool leader = elect_one() != 0;
     uint32_t phase = 0;
     const long long t0 = clock64();
@@ -56,14 +56,14 @@ int main() {
   long long* d; cudaMalloc(&d, 16);
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int n = 6000;
-  for (int ts = 0; ts < 2; ++ts)
-    for (int N : {64, 128, 256})
-      for (int stw : {0, 12})
+  for (int sw = 0; sw < 2; ++sw)
+    for (int ts = 0; ts < 2; ++ts)
+      for (int N : {64, 128, 256})
         for (int pc : {6, 60}) {
-          rate_kernel<<<1, 512, 64 * 1024>>>(d, n, N, ts, stw, pc);
+          rate_kernel<<<1, 512, 64 * 1024>>>(d, n, N, ts, 0, pc, sw);
           cudaError_t e = cudaDeviceSynchronize();
           long long h = 0; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-          printf("%s N=%3d st_warps=%2d mma/commit=%2d : %7.1f clk per MMA (ideal %d)  %s\n", ts ? "TS" : "SS", N, stw, pc,
+          printf("%s %s N=%3d mma/commit=%2d : %7.1f clk per MMA (ideal %d)  %s\n", sw ? "SW128" : "NOSWZ", ts ? "TS" : "SS", N, pc,
                  (double)h / n, N / 2, cudaGetErrorString(e));
         }
   return 0;

@@ -27,6 +27,21 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_noswizzle(uint32_t smem_add
   return d;
 }
 
+// K-major operand in the SWIZZLE_128B layout: rows of 128 bytes (64 fp16), 8-row / 1024-byte atoms,
+// the 16-byte chunk c of row r is stored at chunk position c ^ (r & 7).  SBO = 1024; a K16 step
+// advances the start address by 32 bytes; when the start address is not 1024-byte aligned (row
+// shifts), base_offset = (addr >> 7) & 7.
+__device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                       // LBO (unused for one 64-wide swizzle atom)
+  d |= (uint64_t)(1024 >> 4) << 32;             // SBO
+  d |= 1ull << 46;                              // descriptor version
+  d |= (uint64_t)(base_offset & 7) << 49;
+  d |= 2ull << 61;                              // SWIZZLE_128B
+  return d;
+}
+
 // ---- instruction descriptor, kind::f16 (A,B = f16, D = f32, both operands K-major) -------------
 //   [4,6) D format (1 = f32), [7,10) A format (0 = f16, 1 = bf16), [10,13) B format,
 //   bit 15 A major (0 = K), bit 16 B major (0 = K), [17,23) N>>3, [24,29) M>>4

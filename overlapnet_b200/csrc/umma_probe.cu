@@ -31,6 +31,9 @@ static const char* kModes[] = {
     "6: SS, N=256 (4 x tcgen05.ld.x32 per warp... full TMEM row)",
     "7: SS, N=192 (correlation head shape)",
     "8: TS, N=64, K=128, two A buffers at different TMEM columns (pipelining shape)",
+    "9: SS, SWIZZLE_128B operands (chunk ^ (row&7)), aligned start",
+    "10: SS, SWIZZLE_128B, A start shifted by 5 rows (640 B), base_offset = 0 (diagnostic)",
+    "11: SS, SWIZZLE_128B, A start shifted by 5 rows, base_offset = (addr >> 7) & 7",
 };
 
 __global__ void __launch_bounds__(128, 1)
@@ -52,6 +55,7 @@ probe_kernel(const __half* __restrict__ gA, const __half* __restrict__ gB, float
   const uint32_t tmem = s_tmem;
   const bool ts = (p.mode == 3 || p.mode == 4 || p.mode == 8);
   const bool canonical = (p.mode == 5);
+  const bool sw = (p.mode >= 9);
 
   // ---- stage operands
   if (!ts) {
@@ -59,6 +63,7 @@ probe_kernel(const __half* __restrict__ gA, const __half* __restrict__ gB, float
       const int r = e / K, k = e % K;
       size_t off = canonical ? ((size_t)(r / 8) * (K / 8) + k / 8) * 64 + (r % 8) * 8 + k % 8
                              : ((size_t)(k / 8) * R + r) * 8 + k % 8;
+      if (sw) off = (size_t)r * 64 + (((k / 8) ^ (r & 7)) * 8) + k % 8;       // 128-byte rows, chunk swizzle (K == 64)
       sA[off] = gA[(size_t)r * K + k];
     }
   }
@@ -66,6 +71,7 @@ probe_kernel(const __half* __restrict__ gA, const __half* __restrict__ gB, float
     const int r = e / K, k = e % K;
     size_t off = canonical ? ((size_t)(r / 8) * (K / 8) + k / 8) * 64 + (r % 8) * 8 + k % 8
                            : ((size_t)(k / 8) * N + r) * 8 + k % 8;
+    if (sw) off = (size_t)r * 64 + (((k / 8) ^ (r & 7)) * 8) + k % 8;
     sB[off] = gB[(size_t)r * K + k];
   }
   const uint32_t a_col = 256;          // TMEM columns [256, 256 + K/2) hold A in TS mode
@@ -102,13 +108,18 @@ probe_kernel(const __half* __restrict__ gA, const __half* __restrict__ gB, float
     for (int kb = 0; kb < K / 16; ++kb) {
       const uint32_t k_adv_a = canonical ? kb * 2 * 128 : kb * 2 * R * 16;
       const uint32_t k_adv_b = canonical ? kb * 2 * 128 : kb * 2 * N * 16;
-      const uint64_t bd = make_desc_kmajor_noswizzle(b_base + k_adv_b, b_lbo, b_sbo);
+      uint64_t bd = make_desc_kmajor_noswizzle(b_base + k_adv_b, b_lbo, b_sbo);
+      if (sw) bd = make_desc_kmajor_sw128(b_base + kb * 32, 0);
       if (ts) {
         uint32_t col = a_col + kb * 8;
         if (p.mode == 8 && kb * 8 >= K / 4) col += 64;
         mma_ts(tmem, tmem + col, bd, idesc, kb > 0);
       } else {
-        const uint64_t ad = make_desc_kmajor_noswizzle(a_base + k_adv_a, a_lbo, a_sbo);
+        uint64_t ad = make_desc_kmajor_noswizzle(a_base + k_adv_a, a_lbo, a_sbo);
+        if (sw) {
+          const uint32_t a0 = smem_u32(sA) + p.shift * 128;
+          ad = make_desc_kmajor_sw128(a0 + kb * 32, p.mode == 11 ? ((a0 >> 7) & 7) : 0);
+        }
         mma_ss(tmem, ad, bd, idesc, kb > 0);
       }
     }
@@ -141,11 +152,11 @@ int main(int argc, char** argv) {
   Params p;
   p.mode = atoi(argv[1]);
   p.N = 64; p.K = 64; p.shift = 0; p.a_rows = 128;
-  if (p.mode == 2) { p.shift = 5; p.a_rows = 144; }
+  if (p.mode == 2 || p.mode == 10 || p.mode == 11) { p.shift = 5; p.a_rows = 144; }
   if (p.mode == 6) p.N = 256;
   if (p.mode == 7) p.N = 192;
   if (p.mode == 8) p.K = 128;
-  printf("mode %s\n", p.mode >= 0 && p.mode <= 8 ? kModes[p.mode] : "?");
+  printf("mode %s\n", p.mode >= 0 && p.mode <= 11 ? kModes[p.mode] : "?");
   const int R = p.a_rows, N = p.N, K = p.K;
   std::vector<__half> A((size_t)R * K), B((size_t)N * K);
   std::vector<float> Af((size_t)R * K), Bf((size_t)N * K);
