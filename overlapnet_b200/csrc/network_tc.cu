@@ -43,10 +43,9 @@ constexpr int K4_PITCH = CF + 8;        // fp16 row pitch of L / R for k_delta_c
 
 struct TcState {
   __half* w1p = nullptr;        // [60 steps][4][64][8]
-  __half* w2p = nullptr;        // [30 slabs][4][128][8]
+  __half* w2p = nullptr;        // [15 di][128 n][64 o] SWIZZLE_128B tiles
   __half* w3p = nullptr;        // [2 halves][36 slabs][4][128][8]
-  int* slab2_plane = nullptr; int* slab2_shift = nullptr;     // per-copy (n_slabs*4) tables
-  int* slab3_plane = nullptr; int* slab3_shift = nullptr;
+  float* b2eff = nullptr;       // c_conv2 bias + the c_conv1 bias pushed through W2 (both layers are linear)
   // tensor-core leg (layers 2..): packed weights + copy tables per layer, ping-pong activation planes
   __half* wleg[kMaxLegLayers] = {};      // [1][n_slabs][4][NT][8]   (throughput mode)
   __half* wleg64[kMaxLegLayers] = {};    // [cout/64][n_slabs][4][64][8] (streamed, 64-wide)
@@ -58,8 +57,8 @@ struct TcState {
   __half* actp[2] = {nullptr, nullptr};
   __half* l16 = nullptr;        // [max_pairs][360][128]
   __half* r16 = nullptr;        // [max_pairs][360][128] (pair mode) / [1][360][128] (query mode)
-  __half* o1 = nullptr;         // [120 planes][rows_pad][8]
-  __half* x3 = nullptr;         // [16 planes][rows_pad][8]
+  __half* o1 = nullptr;         // [rows_pad/128][15 di][128][64]: SWIZZLE_128B A tiles of c_conv2 (o1_chunk_offset)
+  __half* x3 = nullptr;         // [16 planes][rows_pad][8], row = pair*576 + jb*24 + ib
   float* partial = nullptr;     // [rows_pad][2]
   __half* lc = nullptr;         // correlation operands: [max_pairs][3 tiles][2 k-halves][hi,lo][8][128][8]
   __half* rc = nullptr;         // [max_pairs or 1][2 n-halves][hi,lo][16][192][8]
@@ -96,27 +95,53 @@ k_gather_rows_f16(const float* __restrict__ bank, const int32_t* __restrict__ id
 // ------------------------------------------------------------------------------------------------
 // k_delta_conv1_tc
 // ------------------------------------------------------------------------------------------------
-constexpr int K4_PROD_WARPS = 12;       // three groups of 4 warps (one per TMEM lane quarter); group g owns steps with step % 3 == g
+#ifndef OVN_K4_GROUPS
+#define OVN_K4_GROUPS 3
+#endif
+constexpr int K4_GROUPS = OVN_K4_GROUPS; // producer groups of 4 warps (one per TMEM lane quarter); group g owns steps with step % K4_GROUPS == g
+constexpr int K4_PROD_WARPS = 4 * K4_GROUPS;
 constexpr int K4_THREADS = (8 + K4_PROD_WARPS) * 32;
 constexpr int K4_STAGES = 6;            // A ring: TMEM column slots
-constexpr int K4_BGROUPS = 4;           // B ring: 4 groups of 6 consecutive W1 slices (24 KB, one bulk copy, one barrier each)
-constexpr int K4_BSLOTS = 24;
+constexpr int K4_BGROUPS = 3;           // B ring: 3 groups of 6 consecutive W1 slices (24 KB, one bulk copy, one barrier each;
+                                        //   4 groups measured no faster, and the 24 KB pay for the epilogue staging)
+constexpr int K4_BSLOTS = K4_BGROUPS * 6;
 constexpr int K4_TILES = 3;
 constexpr int K4_ACOL0 = 192;           // TMEM columns: D = [0,192), A stages = [192, 192 + 6*48)
 constexpr int K4_STAGE_COLS = 48;
 constexpr int K4_STEPS = 60;            // 4 channel chunks x 15 dj per jb
 constexpr int K4_BSLICE = 4096;         // bytes of W1 per step: [4 k8][64 o][8]
 constexpr int K4_RWIN_BYTES = S15 * K4_PITCH * 2;   // the 15 RIGHT rows one jb touches
+constexpr int K4_PHASE_CLK = 2200;      // start stagger of the MMA issuer: 8 phases x 2200 clk ~ one unit (60 steps x ~290 clk)
+
+// o1 layout ("SWIZZLE_128B tiles"): the A operand of c_conv2, stored as the shared-memory image its
+// MMAs read, so that c_conv2 loads a [128 rows x 64 K] tile with ONE 16 KB bulk copy:
+//   row m = pair*576 + jb*24 + ib (i = ib*15 + di), K = di*64 + o
+//   o1[(m / 128) * 15 + di][m % 128][chunk (o/8) ^ (m & 7)][o % 8]
+__host__ __device__ __forceinline__ size_t o1_chunk_offset(int64_t m, int di, int c8) {
+  const int r = (int)(m & 127);
+  return ((size_t)((m >> 7) * S15 + di) * 128 + r) * 64 + (size_t)((c8 ^ (r & 7)) * 8);
+}
 
 struct K4Smem {
   __half L[WF * K4_PITCH];
   __half Rw[2][S15 * K4_PITCH];         // double-buffered RIGHT-row window (streamed per jb)
   __half B[K4_BSLOTS][K4_BSLICE / 2];
-  float bias[64];
+  uint8_t epi[K4_TILES][4][32 * 128];   // [tile][epilogue warp]: 32 fp16 output rows staged for the transposed store
   uint64_t a_full[K4_STAGES], a_empty[K4_STAGES], b_full[K4_BGROUPS], b_empty[K4_BGROUPS];
-  uint64_t d_full, d_empty, l_full, l_empty, rw_full[2], rw_empty[2];
+  uint64_t d_full, d_empty[K4_TILES], l_full, l_empty, rw_full[2], rw_empty[2];
   uint32_t tmem_base;
 };
+
+static_assert(sizeof(K4Smem) <= 232448, "k_delta_conv1_tc shared memory");
+
+// Development aid (tools/k4_trace.py): a build with -DOVN_K4_TRACE records clock64() timestamps of
+// CTA 0's roles for one jb.  Compiled out of the product library.
+#ifdef OVN_K4_TRACE
+__device__ long long g_k4_trace[8][64][4];
+#define K4_TR(cond, role, step, ev, val) do { if ((cond) && blockIdx.x == 0) g_k4_trace[role][step][ev] = (val); } while (0)
+#else
+#define K4_TR(cond, role, step, ev, val) do { } while (0)
+#endif
 
 #define TC_WAIT(bar, parity, code)                       \
   if (!mbar_wait((bar), (parity), kWaitCycles)) {        \
@@ -124,30 +149,37 @@ struct K4Smem {
     goto done;                                           \
   }
 
+// Work unit = (pair, jb): one 360 x 64 block of o1.  Every CTA takes a contiguous range of the
+// n_pairs*24 units (1101 pairs on 148 SMs is 7.44 pairs per SM: whole pairs would leave 7 % idle).
+//
 // Measured on B200 (profiles/r1_*): (1) with W1 slices sharing the 6-deep A ring the kernel was
 // bound by the L2 -> shared round trip of a slice (slot turnaround ~4000 clk), so the W1 ring is
 // separate and 24 deep; (2) that only fits next to the LEFT volume if the RIGHT volume is not
 // resident: a jb touches just 15 RIGHT rows, which are streamed as a 4 KB double-buffered window;
 // (3) a producer warp's LDS -> ALU -> tcgen05.st -> wait::st -> arrive chain runs at IPC ~0.2, so
-// 16 producer warps in two groups work on alternating steps.
-template <int PROD>   // producer organisation: 1 = 3 groups x 4 warps, full K per thread; 0 = 2 groups x 8 warps, half K per thread
-__global__ void __launch_bounds__(PROD == 1 ? 640 : 768, 1)
+// 12 producer warps in three groups work on interleaved steps; (4) the clock64 trace
+// (profiles/r1_k4_trace*.log) showed the issuer at the tensor rate (250 clk per step) in steady
+// state, but stalled ~5000 clk per jb behind the epilogue, whose stores were one 16 B piece per
+// lane per line (32 LSU transactions per instruction): the epilogue now transposes through shared
+// memory and stores whole 128 B lines, and hands the accumulator back tile by tile.
+__global__ void __launch_bounds__(K4_THREADS, 1)
 k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_idx, const __half* __restrict__ R16,
-                 int r_per_pair, const __half* __restrict__ W1p, const float* __restrict__ bias1, __half* __restrict__ o1,
-                 int64_t rows_pad, int n_pairs, int* __restrict__ err) {
+                 int r_per_pair, const __half* __restrict__ W1p, __half* __restrict__ o1, int n_pairs, int* __restrict__ err) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   K4Smem& S = *reinterpret_cast<K4Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_units = (int64_t)n_pairs * NB;
+  const int u_begin = (int)(n_units * blockIdx.x / gridDim.x), u_end = (int)(n_units * (blockIdx.x + 1) / gridDim.x);
 
   if (tid == 0) {
-    for (int s = 0; s < K4_STAGES; ++s) { mbar_init(&S.a_full[s], PROD == 1 ? 4 : 8); mbar_init(&S.a_empty[s], 1); }
+    for (int s = 0; s < K4_STAGES; ++s) { mbar_init(&S.a_full[s], 4); mbar_init(&S.a_empty[s], 1); }
     for (int s = 0; s < K4_BGROUPS; ++s) { mbar_init(&S.b_full[s], 1); mbar_init(&S.b_empty[s], 1); }
-    mbar_init(&S.d_full, 1); mbar_init(&S.d_empty, 4);
-    mbar_init(&S.l_full, 1); mbar_init(&S.l_empty, PROD == 1 ? 12 : 16);
-    for (int b = 0; b < 2; ++b) { mbar_init(&S.rw_full[b], 1); mbar_init(&S.rw_empty[b], PROD == 1 ? 12 : 16); }
+    mbar_init(&S.d_full, 1);
+    for (int t = 0; t < K4_TILES; ++t) mbar_init(&S.d_empty[t], 4);
+    mbar_init(&S.l_full, 1); mbar_init(&S.l_empty, K4_PROD_WARPS);
+    for (int b = 0; b < 2; ++b) { mbar_init(&S.rw_full[b], 1); mbar_init(&S.rw_empty[b], K4_PROD_WARPS); }
     mbar_fence_init();
   }
-  if (tid < 64) S.bias[tid] = bias1[tid];
   if (warp == 2) tmem_alloc(&S.tmem_base, 512);
   fence_before_sync();
   __syncthreads();
@@ -159,128 +191,203 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_i
     // ===================== loader A: W1 through the deep ring, 6 consecutive slices per copy ====
     if (lane == 0) {
       uint32_t bg = 0, bph = 0;
-      for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
-        for (int jb = 0; jb < NB; ++jb) {
-          for (int o = 0; o < K4_STEPS / K4_STAGES; ++o) {
-            TC_WAIT(&S.b_empty[bg], bph ^ 1, 102);
-            mbar_arrive_expect_tx(&S.b_full[bg], K4_STAGES * K4_BSLICE);
-            bulk_g2s(S.B[bg * K4_STAGES], W1p + (size_t)o * K4_STAGES * (K4_BSLICE / 2), K4_STAGES * K4_BSLICE, &S.b_full[bg]);
-            if (++bg == K4_BGROUPS) { bg = 0; bph ^= 1; }
-          }
+      for (int u = u_begin; u < u_end; ++u) {
+        for (int o = 0; o < K4_STEPS / K4_STAGES; ++o) {
+          TC_WAIT(&S.b_empty[bg], bph ^ 1, 102);
+          mbar_arrive_expect_tx(&S.b_full[bg], K4_STAGES * K4_BSLICE);
+          bulk_g2s(S.B[bg * K4_STAGES], W1p + (size_t)o * K4_STAGES * (K4_BSLICE / 2), K4_STAGES * K4_BSLICE, &S.b_full[bg]);
+          if (++bg == K4_BGROUPS) { bg = 0; bph ^= 1; }
         }
       }
     }
   } else if (warp == 3) {
     // ===================== loader B: LEFT volume per pair, RIGHT row window per jb ==============
     if (lane == 0) {
-      uint32_t pi = 0, jbit = 0;
-      for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++pi) {
-        TC_WAIT(&S.l_empty, (pi & 1) ^ 1, 101);
-        mbar_arrive_expect_tx(&S.l_full, VOL_BYTES);
-        bulk_g2s(S.L, L16 + (size_t)(l_idx ? l_idx[p] : p) * WF * K4_PITCH, VOL_BYTES, &S.l_full);
-        const __half* Rp = R16 + (r_per_pair ? (size_t)p * WF * K4_PITCH : 0);
-        for (int jb = 0; jb < NB; ++jb, ++jbit) {
-          const uint32_t b = jbit & 1;
-          TC_WAIT(&S.rw_empty[b], ((jbit >> 1) & 1) ^ 1, 103);
-          mbar_arrive_expect_tx(&S.rw_full[b], K4_RWIN_BYTES);
-          bulk_g2s(S.Rw[b], Rp + (size_t)jb * S15 * K4_PITCH, K4_RWIN_BYTES, &S.rw_full[b]);
+      uint32_t pi = 0, ui = 0;
+      int p = u_begin / NB, jb = u_begin - p * NB;
+      for (int u = u_begin; u < u_end; ++u, ++ui) {
+        if (u == u_begin || jb == 0) {
+          TC_WAIT(&S.l_empty, (pi & 1) ^ 1, 101);
+          mbar_arrive_expect_tx(&S.l_full, VOL_BYTES);
+          bulk_g2s(S.L, L16 + (size_t)(l_idx ? l_idx[p] : p) * WF * K4_PITCH, VOL_BYTES, &S.l_full);
+          ++pi;
         }
+        const __half* Rp = R16 + (r_per_pair ? (size_t)p * WF * K4_PITCH : 0);
+        const uint32_t b = ui & 1;
+        TC_WAIT(&S.rw_empty[b], ((ui >> 1) & 1) ^ 1, 103);
+        mbar_arrive_expect_tx(&S.rw_full[b], K4_RWIN_BYTES);
+        bulk_g2s(S.Rw[b], Rp + (size_t)jb * S15 * K4_PITCH, K4_RWIN_BYTES, &S.rw_full[b]);
+        if (++jb == NB) { jb = 0; ++p; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer ==========================================================
     // Warp-uniform loop (addresses / descriptors stay in uniform registers), one elected lane
     // issues.  The A ring is unrolled (60 steps = 10 x 6 slots: slot offsets are immediates and the
-    // phase is the parity of the outer counter); the B slot is a running counter.
+    // phase is the parity of the outer counter); the B group is a running counter.
     {
       const uint32_t idesc = make_idesc_f16(128, 64);
       const uint64_t bdesc0 = make_desc_kmajor_noswizzle(smem_u32(S.B[0]), 1024, 128);
       const uint32_t bd_hi = (uint32_t)(bdesc0 >> 32), bd_lo = (uint32_t)bdesc0;
       const bool leader = elect_one() != 0;
       // An mbarrier probe costs ~90 clk even when the phase is already complete, and this warp is the
-      // pacemaker: W1 is waited for once per 6 steps (one barrier per 24 KB group) and the A barrier
-      // of step s+1 is probed BEFORE the MMAs of step s are issued, so its latency hides behind them.
-      const uint32_t a_full0 = smem_u32(&S.a_full[0]);
-      uint32_t jbit = 0, bg = 0, bph = 0;
-      for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
-        for (int jb = 0; jb < NB; ++jb, ++jbit) {
-          TC_WAIT(&S.d_empty, (jbit & 1) ^ 1, 201);
-          fence_after_sync();
+      // pacemaker: every barrier it needs (A slot of the next step, W1 group and first A slot of the
+      // next 6-step group) is probed with a non-blocking test_wait one step BEFORE it is needed, so the
+      // probe latency hides behind the MMAs being issued; only a failed probe falls back to a wait.
+      const uint32_t a_full0 = smem_u32(&S.a_full[0]), b_full0 = smem_u32(&S.b_full[0]);
+      uint32_t ui = 0, bg = 0, bph = 0;
+      bool ready = false, bready = false;
+      {
+        // All CTAs run the same schedule, so without a phase offset their epilogues store 46 KB each
+        // at the same instant (a 6.8 MB burst every unit, measured at ~16 B/clk/SM: the issuer then
+        // waits ~4000 clk for its accumulators).  Eight start phases spread the bursts over the unit.
+        const long long t_go = clock64() + (long long)(blockIdx.x & 7) * K4_PHASE_CLK;
+        while (clock64() < t_go) { }
+      }
+      for (int u = u_begin; u < u_end; ++u, ++ui) {
 #pragma unroll 1
-          for (uint32_t o = 0; o < K4_STEPS / K4_STAGES; ++o) {
-            const uint32_t ph = o & 1;            // (step / 6) & 1: steps per jb (60) and per pair are multiples of 12
-            TC_WAIT(&S.b_full[bg], bph, 203);
-            bool ready = mbar_try_wait_addr(a_full0, ph);
-            const uint32_t b_lo = bd_lo + ((bg * K4_STAGES * K4_BSLICE) >> 4);
+        for (uint32_t o = 0; o < K4_STEPS / K4_STAGES; ++o) {
+          const uint32_t ph = o & 1;            // (step / 6) & 1: 10 groups per unit
+          if (!bready) { if (!mbar_wait_addr(b_full0 + bg * 8, bph, kWaitCycles)) { atomicExch(err, 203); goto done; } }
+          const uint32_t b_lo = bd_lo + ((bg * K4_STAGES * K4_BSLICE) >> 4);
+          const uint32_t nbg = (bg + 1 == K4_BGROUPS) ? 0 : bg + 1, nbph = (bg + 1 == K4_BGROUPS) ? bph ^ 1 : bph;
 #pragma unroll
-            for (int sg = 0; sg < K4_STAGES; ++sg) {
-              if (!ready) { if (!mbar_wait_addr(a_full0 + sg * 8, ph, kWaitCycles)) { atomicExch(err, 202); goto done; } }
-              if (sg + 1 < K4_STAGES) ready = mbar_try_wait_addr(a_full0 + (sg + 1) * 8, ph);   // probe ahead
-              fence_after_sync();
-              if (leader) {
-                // consecutive MMAs go to different accumulator tiles (no back-to-back dependency on one D)
+          for (int sg = 0; sg < K4_STAGES; ++sg) {
+            K4_TR(leader && u == u_begin + 2, 0, o * 6 + sg, 0, clock64());
+            K4_TR(leader && u == u_begin + 2, 0, o * 6 + sg, 3, (long long)ready);
+            if (!ready) { if (!mbar_wait_addr(a_full0 + sg * 8, ph, kWaitCycles)) { atomicExch(err, 202); goto done; } }
+            K4_TR(leader && u == u_begin + 2, 0, o * 6 + sg, 1, clock64());
+            // non-blocking probes ahead
+            if (sg + 1 < K4_STAGES) ready = mbar_test_addr(a_full0 + (sg + 1) * 8, ph);
+            else ready = mbar_test_addr(a_full0, ph ^ 1);
+            if (sg == K4_STAGES - 2) bready = mbar_test_addr(b_full0 + nbg * 8, nbph);
+            fence_after_sync();
+            if (sg == 0 && o == 0) {
+              // D is single-buffered (TMEM is full): the first step of a unit is issued tile by tile,
+              // each tile as soon as the epilogue has pulled that tile of the previous unit into
+              // registers.  (Running the first six steps tile-major was measured slower: the producers
+              // have only just been given the six slots back and tile 0 then waits for slot 5.)
+              for (int t = 0; t < K4_TILES; ++t) {
+                TC_WAIT(&S.d_empty[t], (ui & 1) ^ 1, 201);
+                fence_after_sync();
+                if (leader) {
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                  const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_lo + ((sg * K4_BSLICE + kk * 2048) >> 4));
-#pragma unroll
-                  for (int t = 0; t < K4_TILES; ++t) {
-                    mma_ts(tmem + t * 64, tmem + K4_ACOL0 + sg * K4_STAGE_COLS + t * 16 + kk * 8, bd, idesc,
-                           (o | (uint32_t)sg | (uint32_t)kk) != 0);
+                  for (int kk = 0; kk < 2; ++kk) {
+                    const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_lo + ((kk * 2048) >> 4));
+                    mma_ts(tmem + t * 64, tmem + K4_ACOL0 + t * 16 + kk * 8, bd, idesc, kk != 0);
                   }
                 }
-                commit(&S.a_empty[sg]);
-                if (sg == K4_STAGES - 1) commit(&S.b_empty[bg]);
+                __syncwarp();
               }
+              if (leader) commit(&S.a_empty[0]);
+              K4_TR(leader && u == u_begin + 2, 0, 0, 2, clock64());
               __syncwarp();
+              continue;
             }
-            if (++bg == K4_BGROUPS) { bg = 0; bph ^= 1; }
+            if (leader) {
+              // consecutive MMAs go to different accumulator tiles
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {
+                const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_lo + ((sg * K4_BSLICE + kk * 2048) >> 4));
+#pragma unroll
+                for (int t = 0; t < K4_TILES; ++t) {
+                  mma_ts(tmem + t * 64, tmem + K4_ACOL0 + sg * K4_STAGE_COLS + t * 16 + kk * 8, bd, idesc, 1);
+                }
+              }
+              commit(&S.a_empty[sg]);
+              if (sg == K4_STAGES - 1) commit(&S.b_empty[bg]);
+            }
+            K4_TR(leader && u == u_begin + 2, 0, o * 6 + sg, 2, clock64());
+            __syncwarp();
           }
-          if (leader) commit(&S.d_full);
-          __syncwarp();
+          bg = nbg; bph = nbph;
         }
+        if (leader) commit(&S.d_full);
+        __syncwarp();
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    // ===================== epilogue: D (TMEM) -> +bias -> fp16 -> o1 planes ====================
+    // ===================== epilogue: D (TMEM) -> fp16 -> o1 tiles ================================
+    // Lane = output row i.  A row is 64 channels = one 128 B line of o1; written lane-per-row the 8
+    // STG.128 of a warp would each touch 32 lines.  The warp transposes its 32 rows through shared
+    // memory instead, so that 8 lanes cover one line and an instruction stores 4 whole lines.
+    // (Measured alternatives: one 128 B bulk shared->global copy per lane is slower -- the copy
+    // engine takes ~18 clk per small copy; STG itself tops out near 32 B/clk/SM.)
     const int q = warp & 3;
-    uint32_t jbit = 0;
-    for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
-      for (int jb = 0; jb < NB; ++jb, ++jbit) {
-        TC_WAIT(&S.d_full, jbit & 1, 301);
-        fence_after_sync();
+    uint32_t ui = 0;
+    int p = u_begin / NB, jb = u_begin - p * NB;
+    for (int u = u_begin; u < u_end; ++u, ++ui) {
+      K4_TR(q == 0 && lane == 0 && u == u_begin + 1, 4, 0, 0, clock64());
+      TC_WAIT(&S.d_full, ui & 1, 301);
+      fence_after_sync();
+      K4_TR(q == 0 && lane == 0 && u == u_begin + 1, 4, 0, 1, clock64());
+      const int64_t m0 = (int64_t)p * PAIR_ROWS + jb * NB;
+      // pass 1: pull the three accumulator tiles out of TMEM as fast as possible (the MMA issuer is
+      // waiting for them): tcgen05.ld -> release -> fp16 -> staging buffer t (row = lane, 16-byte
+      // chunks XOR-swizzled by the row so that both passes are bank-conflict free without padding)
 #pragma unroll 1
-        for (int t = 0; t < K4_TILES; ++t) {
-          const int i = t * 128 + q * 32 + lane;
-          const int ib = i / S15, di = i - ib * S15;
-          const int64_t m = (int64_t)p * PAIR_ROWS + ib * NB + jb;
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + t * 64 + c * 32, v);
-            tmem_ld_wait();
-            if (t == K4_TILES - 1 && c == 1) {   // everything is in registers: hand D back before the stores
-              fence_before_sync();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&S.d_empty);
-            }
-            if (i < WF) {
+      for (int t = 0; t < K4_TILES; ++t) {
+        uint32_t v0[32], v1[32];
+        K4_TR(q == 0 && lane == 0 && u == u_begin + 1, 4, 1 + t, 1, clock64());
+        tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + t * 64, v0);
+        tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + t * 64 + 32, v1);
+        tmem_ld_wait();
+        fence_before_sync();                 // this tile is in registers: hand it back to the MMA issuer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.d_empty[t]);
+        K4_TR(q == 0 && lane == 0 && u == u_begin + 1, 4, 1 + t, 0, clock64());
+        // (the c_conv1 bias is folded into the c_conv2 bias at pack time: both layers are linear)
+        uint8_t* row = S.epi[t][q] + lane * 128;
 #pragma unroll
-              for (int h8 = 0; h8 < 4; ++h8) {
-                uint32_t pk[4];
+        for (int c = 0; c < 2; ++c) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int o = c * 32 + h8 * 8 + 2 * j;
-                  __half2 hh = __floats2half2_rn(__uint_as_float(v[h8 * 8 + 2 * j]) + S.bias[o],
-                                                 __uint_as_float(v[h8 * 8 + 2 * j + 1]) + S.bias[o + 1]);
-                  pk[j] = *reinterpret_cast<uint32_t*>(&hh);
-                }
-                const int k8 = di * 8 + c * 4 + h8;               // plane = (di, o/8)
-                *reinterpret_cast<uint4*>(o1 + ((size_t)k8 * rows_pad + m) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              }
+          for (int h8 = 0; h8 < 4; ++h8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t a = c ? v1[h8 * 8 + 2 * j] : v0[h8 * 8 + 2 * j];
+              const uint32_t b = c ? v1[h8 * 8 + 2 * j + 1] : v0[h8 * 8 + 2 * j + 1];
+              __half2 hh = __floats2half2_rn(__uint_as_float(a), __uint_as_float(b));
+              pk[j] = *reinterpret_cast<uint32_t*>(&hh);
             }
+            *reinterpret_cast<uint4*>(row + (((c * 4 + h8) ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
+        K4_TR(q == 0 && lane == 0 && u == u_begin + 1, 4, 1 + t, 3, clock64());
       }
+      __syncwarp();
+      // pass 2 (overlaps the MMAs of the next unit): transposed stores, 8 lanes per 128 B line.
+      // lane -> (row rr0 + 4k, chunk c8); (ib, di) advance incrementally, the address is counted in
+      // 16-byte chunks: (((m >> 7) * 15 + di) << 10) | ((m & 127) << 3) | (c8 ^ (m & 7)), m0 % 8 == 0
+#pragma unroll 1
+      for (int t = 0; t < K4_TILES; ++t) {
+        const int c8 = lane & 7, rr0 = lane >> 3;
+        int i = t * 128 + q * 32 + rr0;
+        int ib = i / S15, di = i - ib * S15;
+        const uint8_t* src = S.epi[t][q] + rr0 * 128;
+        uint4* const o1c = reinterpret_cast<uint4*>(o1);
+        // branch-free and batched (all loads, then all stores): one warp per scheduler has nothing
+        // else to hide the LDS -> address -> STG chain behind
+        uint4 v[8];
+        size_t chunk[8];
+        bool ok[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          v[k] = *reinterpret_cast<const uint4*>(src + k * 512 + ((c8 ^ ((rr0 + 4 * k) & 7)) << 4));
+          const int64_t m = m0 + ib;
+          chunk[k] = ((size_t)((m >> 7) * S15 + di) << 10) | (size_t)(((int)m & 127) << 3) | (size_t)(c8 ^ (ib & 7));
+          ok[k] = i < WF;
+          i += 4; di += 4;
+          if (di >= S15) { di -= S15; ++ib; }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)     // predicated (not branched) stores keep the eight chains independent
+          asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p st.global.v4.b32 [%0], {%1, %2, %3, %4}; }"
+                       :: "l"(o1c + chunk[k]), "r"(v[k].x), "r"(v[k].y), "r"(v[k].z), "r"(v[k].w), "r"((uint32_t)ok[k]) : "memory");
+        K4_TR(q == 0 && lane == 0 && u == u_begin + 1, 4, 1 + t, 2, clock64());
+      }
+      __syncwarp();                          // staging buffers are rewritten by the next unit's pass 1
+      if (++jb == NB) { jb = 0; ++p; }
     }
   } else if (warp >= 8) {
     // ===================== producers: |l - r| -> TMEM ==========================================
@@ -290,133 +397,77 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_i
     // multiples of 3: dj = g, g+3, ...) into ring slots g, g+3: per synthesised element this costs
     // 1 ALU instruction + ~0.3 of loop / barrier overhead, and a group has three MMA stage-times
     // to hide its LDS -> ALU -> tcgen05.st -> wait::st -> arrive chain.
-    if constexpr (PROD == 1) {
     const int pw = warp - 8, q = pw & 3, grp = pw >> 2;
     const int row0 = q * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + K4_ACOL0;
     const uint32_t a_empty0 = smem_u32(&S.a_empty[0]), a_full0 = smem_u32(&S.a_full[0]);
-    uint32_t pi = 0, jbit = 0, n = 0;       // n: steps produced by this group: slot = grp + 3*(n&1), phase = (n>>1)&1
-    bool slot_free = true;                  // result of the probe issued one step ahead (the first two steps find fresh slots)
-    for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++pi) {
-      TC_WAIT(&S.l_full, pi & 1, 402);
-      for (int jb = 0; jb < NB; ++jb, ++jbit) {
-        const uint32_t wb = jbit & 1;
-        TC_WAIT(&S.rw_full[wb], (jbit >> 1) & 1, 404);
+    uint32_t pi = 0, ui = 0;
+    bool slot_free = true;                  // result of the probe issued one step ahead (the first steps find fresh slots)
+    int jb = u_begin % NB;
+    for (int u = u_begin; u < u_end; ++u, ++ui) {
+      if (u == u_begin || jb == 0) { TC_WAIT(&S.l_full, pi & 1, 402); ++pi; }
+      const uint32_t wb = ui & 1;
+      TC_WAIT(&S.rw_full[wb], (ui >> 1) & 1, 404);
+      int st = grp;                         // step within the unit: slot = st % 6, phase = (st / 6) & 1 (10 ring turns per unit)
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          const int ch = cc * 32;
-          uint32_t Lr[K4_TILES][16];
+      for (int cc = 0; cc < 4; ++cc) {
+        const int ch = cc * 32;
+        uint32_t Lr[K4_TILES][16];
 #pragma unroll
-          for (int t = 0; t < K4_TILES; ++t) {
-            const int i = t * 128 + row0;
+        for (int t = 0; t < K4_TILES; ++t) {
+          const int i = t * 128 + row0;
 #pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) {
-              uint4 a = make_uint4(0u, 0u, 0u, 0u);
-              if (i < WF) a = *reinterpret_cast<const uint4*>(&S.L[i * K4_PITCH + ch + v4 * 8]);
-              Lr[t][v4 * 4 + 0] = a.x; Lr[t][v4 * 4 + 1] = a.y; Lr[t][v4 * 4 + 2] = a.z; Lr[t][v4 * 4 + 3] = a.w;
-            }
-          }
-#pragma unroll 1
-          for (int dj = grp; dj < S15; dj += 3, ++n) {
-            const uint32_t sg = grp + 3 * (n & 1), ph = (n >> 1) & 1;
-            const __half* rrow = &S.Rw[wb][dj * K4_PITCH + ch];
-            if (!slot_free) { if (!mbar_wait_addr(a_empty0 + sg * 8, ph ^ 1, kWaitCycles)) { atomicExch(err, 403); goto done; } }
-            {
-              // probe the slot of this group's NEXT step now; the ~90 clk answer is consumed next iteration
-              const uint32_t n1 = n + 1, sg1 = grp + 3 * (n1 & 1), ph1 = (n1 >> 1) & 1;
-              slot_free = mbar_try_wait_addr(a_empty0 + sg1 * 8, ph1 ^ 1);
-            }
-            fence_after_sync();
-#pragma unroll
-            for (int hk = 0; hk < 2; ++hk) {          // two 16-channel halves: keeps the live set of r at 8 registers
-              const uint4 ra = *reinterpret_cast<const uint4*>(rrow + hk * 16);        // broadcast LDS
-              const uint4 rb = *reinterpret_cast<const uint4*>(rrow + hk * 16 + 8);
-              const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-#pragma unroll
-              for (int t = 0; t < K4_TILES; ++t) {
-                uint32_t o[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  // |l - r|: subtract on the FMA pipe, clear both sign bits on the ALU pipe (LOP3)
-                  const __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&Lr[t][hk * 8 + j]),
-                                            *reinterpret_cast<const __half2*>(&rw[j]));
-                  o[j] = *reinterpret_cast<const uint32_t*>(&d) & 0x7fff7fffu;
-                }
-                tmem_st_x8(lane_addr + sg * K4_STAGE_COLS + t * 16 + hk * 8, o);
-              }
-            }
-            tmem_st_wait();
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_addr(a_full0 + sg * 8);
+          for (int v4 = 0; v4 < 4; ++v4) {
+            uint4 a = make_uint4(0u, 0u, 0u, 0u);
+            if (i < WF) a = *reinterpret_cast<const uint4*>(&S.L[i * K4_PITCH + ch + v4 * 8]);
+            Lr[t][v4 * 4 + 0] = a.x; Lr[t][v4 * 4 + 1] = a.y; Lr[t][v4 * 4 + 2] = a.z; Lr[t][v4 * 4 + 3] = a.w;
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S.rw_empty[wb]);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&S.l_empty);
-    }
-    } else {
-      // 16 warps = 2 groups x (4 TMEM lane quarters x 2 K halves); group g produces steps with step % 2 == g
-      const int pw = warp - 8, q = pw & 3, half = (pw >> 2) & 1, grp = pw >> 3;
-      const int row0 = q * 32 + lane;
-      const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + K4_ACOL0 + half * 8;
-      const uint32_t a_empty0 = smem_u32(&S.a_empty[0]), a_full0 = smem_u32(&S.a_full[0]);
-      uint32_t pi = 0, jbit = 0, sg = grp, ph = 0;
-      for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++pi) {
-        TC_WAIT(&S.l_full, pi & 1, 402);
-        for (int jb = 0; jb < NB; ++jb, ++jbit) {
-          const uint32_t wb = jbit & 1;
-          TC_WAIT(&S.rw_full[wb], (jbit >> 1) & 1, 404);
 #pragma unroll 1
-          for (int cc = 0; cc < 4; ++cc) {
-            const int ch = cc * 32 + half * 16;
-            uint32_t Lr[K4_TILES][8];
+        for (; st < (cc + 1) * S15; st += K4_GROUPS) {
+          const int dj = st - cc * S15;
+          const uint32_t sg = (uint32_t)st % K4_STAGES, ph = ((uint32_t)st / K4_STAGES) & 1;
+          const __half* rrow = &S.Rw[wb][dj * K4_PITCH + ch];
+          K4_TR(q == 0 && lane == 0 && u == u_begin + 2 && grp < 3, 1 + grp, st, 0, clock64());
+          if (!slot_free) { if (!mbar_wait_addr(a_empty0 + sg * 8, ph ^ 1, kWaitCycles)) { atomicExch(err, 403); goto done; } }
+          K4_TR(q == 0 && lane == 0 && u == u_begin + 2 && grp < 3, 1 + grp, st, 1, clock64());
+          {
+            // probe the slot of this group's NEXT step now; the ~90 clk answer is consumed next iteration
+            const uint32_t s1 = (uint32_t)st + K4_GROUPS, sg1 = s1 % K4_STAGES, ph1 = (s1 / K4_STAGES) & 1;
+            slot_free = mbar_test_addr(a_empty0 + sg1 * 8, ph1 ^ 1);
+          }
+          fence_after_sync();
+#pragma unroll
+          for (int hk = 0; hk < 2; ++hk) {          // two 16-channel halves: keeps the live set of r at 8 registers
+            const uint4 ra = *reinterpret_cast<const uint4*>(rrow + hk * 16);        // broadcast LDS
+            const uint4 rb = *reinterpret_cast<const uint4*>(rrow + hk * 16 + 8);
+            const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
             for (int t = 0; t < K4_TILES; ++t) {
-              const int i = t * 128 + row0;
-              uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
-              if (i < WF) {
-                a = *reinterpret_cast<const uint4*>(&S.L[i * K4_PITCH + ch]);
-                b = *reinterpret_cast<const uint4*>(&S.L[i * K4_PITCH + ch + 8]);
-              }
-              Lr[t][0] = a.x; Lr[t][1] = a.y; Lr[t][2] = a.z; Lr[t][3] = a.w;
-              Lr[t][4] = b.x; Lr[t][5] = b.y; Lr[t][6] = b.z; Lr[t][7] = b.w;
-            }
-#pragma unroll 1
-            for (int dj = (grp + cc) & 1; dj < S15; dj += 2) {
-              const __half* rrow = &S.Rw[wb][dj * K4_PITCH + ch];
-              const uint4 ra = *reinterpret_cast<const uint4*>(rrow);
-              const uint4 rb = *reinterpret_cast<const uint4*>(rrow + 8);
-              const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-              if (!mbar_wait_addr(a_empty0 + sg * 8, ph ^ 1, kWaitCycles)) { atomicExch(err, 403); goto done; }
-              fence_after_sync();
+              uint32_t o[8];
 #pragma unroll
-              for (int t = 0; t < K4_TILES; ++t) {
-                uint32_t o[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&Lr[t][j]),
-                                            *reinterpret_cast<const __half2*>(&rw[j]));
-                  o[j] = *reinterpret_cast<const uint32_t*>(&d) & 0x7fff7fffu;
-                }
-                tmem_st_x8(lane_addr + sg * K4_STAGE_COLS + t * 16, o);
+              for (int j = 0; j < 8; ++j) {
+                // |l - r|: subtract on the FMA pipe, clear both sign bits on the ALU pipe (LOP3)
+                const __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&Lr[t][hk * 8 + j]),
+                                          *reinterpret_cast<const __half2*>(&rw[j]));
+                o[j] = *reinterpret_cast<const uint32_t*>(&d) & 0x7fff7fffu;
               }
-              tmem_st_wait();
-              fence_before_sync();
-              __syncwarp();
-              if (lane == 0) mbar_arrive_addr(a_full0 + sg * 8);
-              sg += 2;
-              if (sg >= K4_STAGES) { sg -= K4_STAGES; ph ^= 1; }
+              tmem_st_x8(lane_addr + sg * K4_STAGE_COLS + t * 16 + hk * 8, o);
             }
           }
+          K4_TR(q == 0 && lane == 0 && u == u_begin + 2 && grp < 3, 1 + grp, st, 2, clock64());
+          tmem_st_wait();
+          fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&S.rw_empty[wb]);
+          if (lane == 0) mbar_arrive_addr(a_full0 + sg * 8);
+          K4_TR(q == 0 && lane == 0 && u == u_begin + 2 && grp < 3, 1 + grp, st, 3, clock64());
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S.l_empty);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.rw_empty[wb]);
+      const bool last_of_pair = (jb == NB - 1) || (u == u_end - 1);
+      if (last_of_pair) { __syncwarp(); if (lane == 0) mbar_arrive(&S.l_empty); }
+      if (++jb == NB) jb = 0;
     }
   }
 done:
@@ -654,6 +705,131 @@ done:
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_conv2_sw_tc -- c_conv2 (15x1 stride 15, 64 -> 128, ReLU) as a GEMM  [M x 960] x [960 x 128].
+// k_delta_conv1_tc leaves o1 as ready-made SWIZZLE_128B operand tiles (o1_chunk_offset), so a
+// K step of 64 (= one di) is three 16 KB bulk copies: two A row tiles and the W2 tile they share.
+// Rows are (pair, jb, ib); the ReLU'd result goes to the x3 planes c_conv3 reads.
+// ------------------------------------------------------------------------------------------------
+constexpr int C2_STAGES = 4, C2_TILE_BYTES = 128 * 128;
+
+struct C2Smem;
+struct C2Smem {
+  uint8_t st[C2_STAGES][3][C2_TILE_BYTES];     // [A tile 0][A tile 1][W2 tile]
+  float bias[128];
+  uint64_t full[C2_STAGES], empty[C2_STAGES], d_full[2], d_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+k_conv2_sw_tc(const __half* __restrict__ o1, const __half* __restrict__ W2s, const float* __restrict__ bias2,
+              __half* __restrict__ x3, int64_t out_pitch, int64_t M, int n_iter, int* __restrict__ err) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  C2Smem& S = *reinterpret_cast<C2Smem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < C2_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&S.d_full[b], 1); mbar_init(&S.d_empty[b], 4); }
+    mbar_fence_init();
+  }
+  if (tid < 128) S.bias[tid] = bias2[tid];
+  if (warp == 2) tmem_alloc(&S.tmem_base, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
+        for (int di = 0; di < S15; ++di) {
+          TC_WAIT(&S.empty[s], ph ^ 1, 501);
+          mbar_arrive_expect_tx(&S.full[s], 3 * C2_TILE_BYTES);
+          bulk_g2s(S.st[s][0], o1 + ((size_t)(2 * it) * S15 + di) * (C2_TILE_BYTES / 2), C2_TILE_BYTES, &S.full[s]);
+          bulk_g2s(S.st[s][1], o1 + ((size_t)(2 * it + 1) * S15 + di) * (C2_TILE_BYTES / 2), C2_TILE_BYTES, &S.full[s]);
+          bulk_g2s(S.st[s][2], W2s + (size_t)di * (C2_TILE_BYTES / 2), C2_TILE_BYTES, &S.full[s]);
+          if (++s == C2_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_f16(128, 128);
+    const bool leader = elect_one() != 0;
+    const uint64_t d0 = make_desc_kmajor_sw128(smem_u32(S.st[0][0]), 0);
+    const uint32_t d_hi = (uint32_t)(d0 >> 32), d_lo = (uint32_t)d0;
+    uint32_t s = 0, ph = 0, li = 0;
+    for (int it = blockIdx.x; it < n_iter; it += gridDim.x, ++li) {
+      const uint32_t buf = li & 1;
+      TC_WAIT(&S.d_empty[buf], ((li >> 1) & 1) ^ 1, 502);
+      fence_after_sync();
+#pragma unroll 1
+      for (int di = 0; di < S15; ++di) {
+        TC_WAIT(&S.full[s], ph, 503);
+        fence_after_sync();
+        if (leader) {
+          const uint32_t base = d_lo + ((s * 3 * C2_TILE_BYTES) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {            // 16 K values = 32 B inside the 128 B swizzle row
+            const uint64_t bd = ((uint64_t)d_hi << 32) | (uint64_t)(base + ((2 * C2_TILE_BYTES + kk * 32) >> 4));
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const uint64_t ad = ((uint64_t)d_hi << 32) | (uint64_t)(base + ((t * C2_TILE_BYTES + kk * 32) >> 4));
+              mma_ss(tmem + buf * 256 + t * 128, ad, bd, idesc, (di | kk) != 0);
+            }
+          }
+          commit(&S.empty[s]);
+        }
+        __syncwarp();
+        if (++s == C2_STAGES) { s = 0; ph ^= 1; }
+      }
+      if (leader) commit(&S.d_full[buf]);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    uint32_t li = 0;
+    for (int it = blockIdx.x; it < n_iter; it += gridDim.x, ++li) {
+      const uint32_t buf = li & 1;
+      TC_WAIT(&S.d_full[buf], (li >> 1) & 1, 504);
+      fence_after_sync();
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int64_t m = ((int64_t)(2 * it + t) * 128) + q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + buf * 256 + t * 128 + c0, v);
+          tmem_ld_wait();
+          if (t == 1 && c0 == 96) {                    // both tiles of this buffer are in registers / stored
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.d_empty[buf]);
+          }
+          if (m < M) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int c = c0 + j8 * 8 + 2 * j;
+                __half2 hh = __floats2half2_rn(fmaxf(__uint_as_float(v[j8 * 8 + 2 * j]) + S.bias[c], 0.f),
+                                               fmaxf(__uint_as_float(v[j8 * 8 + 2 * j + 1]) + S.bias[c + 1], 0.f));
+                pk[j] = *reinterpret_cast<uint32_t*>(&hh);
+              }
+              *reinterpret_cast<uint4*>(x3 + ((size_t)(c0 / 8 + j8) * out_pitch + m) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+      }
+    }
+  }
+done:
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_conv3_resident_tc -- c_conv3 (3x3, 128 -> 256, ReLU) + Flatten + Dense partial sums.
 // The streamed GEMM re-reads the activation tile for each of the 9 taps and both N halves
 // (3.6 GB of L2 traffic per 1101 pairs: L2-bound).  Here the 16 activation planes of a 512-row tile
@@ -754,7 +930,8 @@ k_conv3_resident_tc(const __half* __restrict__ X3, int64_t a_pitch, const __half
       const int rem = (int)(r % PAIR_ROWS);
       const int yy = rem / NB, xx = rem - yy * NB;
       const bool valid = (r < M) && (yy < NB - 2) && (xx < NB - 2);
-      const float* wrow = wd + ((size_t)(valid ? (yy * (NB - 2) + xx) : 0) * 256 + nh * 128);
+      // rows are (pair, jb, ib): yy = jb, xx = ib; Flatten order of the reference is (ib, jb, channel)
+      const float* wrow = wd + ((size_t)(valid ? (xx * (NB - 2) + yy) : 0) * 256 + nh * 128);
       float acc = 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 16) {
@@ -1250,7 +1427,7 @@ static int tc_supported(const ovn_handle* h) {
 void tc_free(ovn_handle* h) {
   TcState* t = h->tc;
   if (!t) return;
-  void* bufs[] = {t->w1p, t->w2p, t->w3p, t->slab2_plane, t->slab2_shift, t->slab3_plane, t->slab3_shift,
+  void* bufs[] = {t->w1p, t->w2p, t->w3p, t->b2eff,
                   t->l16, t->r16, t->o1, t->x3, t->partial, t->d_err, t->lc, t->rc, t->corr_part};
   for (void* b : bufs) if (b) cudaFree(b);
   for (int l = 0; l < kMaxLegLayers; ++l) {
@@ -1295,43 +1472,46 @@ int tc_pack_weights(ovn_handle* h) {
             p1[((((size_t)(cc * S15 + dj) * 4 + k8) * 64 + o) * 8) + e] =
                 __float2half(w1.kernel[((size_t)dj * CF + c) * 64 + o]);
           }
-  // c_conv2: K index k = di*64 + o, plane k8 = di*8 + o/8; slab = 4 planes; B[sl][j][n][e] = W2[di][o][n]
-  std::vector<__half> p2((size_t)30 * 4 * 128 * 8);
-  std::vector<int> s2p(30 * 4), s2s(30 * 4, 0);
-  for (int sl = 0; sl < 30; ++sl) {
-    for (int j = 0; j < 4; ++j) {
-      s2p[sl * 4 + j] = sl * 4 + j;
-      const int k8 = sl * 4 + j, di = k8 / 8, o8 = k8 % 8;
-      for (int n = 0; n < 128; ++n)
-        for (int e = 0; e < 8; ++e)
-          p2[(((size_t)sl * 4 + j) * 128 + n) * 8 + e] = __float2half(w2.kernel[((size_t)di * 64 + o8 * 8 + e) * 128 + n]);
-    }
-  }
-  // c_conv3: slab = (dy, dx, channel group g of 32); planes c8 = g*4..g*4+3 of X3; shift = dy*24 + dx
+  // c_conv2: one SWIZZLE_128B tile per di: W2s[di][n][chunk (o/8) ^ (n & 7)][o % 8] = W2[di][o][n]
+  std::vector<__half> p2((size_t)S15 * 128 * 64);
+  for (int di = 0; di < S15; ++di)
+    for (int n = 0; n < 128; ++n)
+      for (int o = 0; o < 64; ++o)
+        p2[((size_t)di * 128 + n) * 64 + (((o >> 3) ^ (n & 7)) << 3) + (o & 7)] =
+            __float2half(w2.kernel[((size_t)di * 64 + o) * 128 + n]);
+  // c_conv3: slab = (tap, channel group g of 32); planes c8 = g*4..g*4+3 of X3.  The x3 image is
+  // stored transposed (row = jb*24 + ib), so the slab applied at row shift a*24 + b holds the kernel
+  // tap (dy = b, dx = a) of the reference's (ib, jb) image.
   std::vector<__half> p3((size_t)2 * 36 * 4 * 128 * 8);
-  std::vector<int> s3p(36 * 4), s3s(36 * 4);
   for (int dy = 0; dy < 3; ++dy)
     for (int dx = 0; dx < 3; ++dx)
       for (int gq = 0; gq < 4; ++gq) {
         const int sl = (dy * 3 + dx) * 4 + gq;
-        for (int j = 0; j < 4; ++j) { s3p[sl * 4 + j] = gq * 4 + j; s3s[sl * 4 + j] = dy * NB + dx; }
         for (int nh = 0; nh < 2; ++nh)
           for (int j = 0; j < 4; ++j)
             for (int n = 0; n < 128; ++n)
               for (int e = 0; e < 8; ++e) {
                 const int c = (gq * 4 + j) * 8 + e;
                 p3[((((size_t)nh * 36 + sl) * 4 + j) * 128 + n) * 8 + e] =
-                    __float2half(w3.kernel[(((size_t)dy * 3 + dx) * 128 + c) * 256 + nh * 128 + n]);
+                    __float2half(w3.kernel[(((size_t)dx * 3 + dy) * 128 + c) * 256 + nh * 128 + n]);
               }
       }
+  // k_delta_conv1_tc stores o1 without the c_conv1 bias; its image under c_conv2 is a constant per channel
+  std::vector<float> b2e(128);
+  {
+    const LayerWeights& wb1 = h->host_w["c_conv1"];
+    for (int n = 0; n < 128; ++n) {
+      double acc = w2.bias[n];
+      for (int di = 0; di < S15; ++di)
+        for (int o = 0; o < 64; ++o) acc += (double)wb1.bias[o] * (double)w2.kernel[((size_t)di * 64 + o) * 128 + n];
+      b2e[n] = (float)acc;
+    }
+  }
   int rc;
+  if ((rc = upload_vec(h, &t->b2eff, b2e)) != OVN_OK) return rc;
   if ((rc = upload_vec(h, &t->w1p, p1)) != OVN_OK) return rc;
   if ((rc = upload_vec(h, &t->w2p, p2)) != OVN_OK) return rc;
   if ((rc = upload_vec(h, &t->w3p, p3)) != OVN_OK) return rc;
-  if ((rc = upload_vec(h, &t->slab2_plane, s2p)) != OVN_OK) return rc;
-  if ((rc = upload_vec(h, &t->slab2_shift, s2s)) != OVN_OK) return rc;
-  if ((rc = upload_vec(h, &t->slab3_plane, s3p)) != OVN_OK) return rc;
-  if ((rc = upload_vec(h, &t->slab3_shift, s3s)) != OVN_OK) return rc;
   // ---- leg layers 2.. : copy e = (dh, dw, c8) -> plane dh*C8in + c8 of the run, row shift dw
   size_t max_planes_bytes = 0;
   for (int l = 0; l < h->n_leg; ++l) {
@@ -1405,7 +1585,7 @@ int tc_pack_weights(ovn_handle* h) {
     OVN_CUDA(h, cudaMemset(t->actp[b], 0, bytes));
   }
   const int64_t maxp = h->cfg.max_batch_pairs;
-  t->rows_pad = maxp * PAIR_ROWS + 1024;           // tile overrun (512) + window shift (50) slack
+  t->rows_pad = ((maxp * PAIR_ROWS + 1024 + 255) / 256) * 256;   // tile overrun (512) + window shift (50) slack; whole c_conv2 tile pairs
   OVN_CUDA(h, cudaMalloc(&t->l16, (size_t)maxp * WF * K4_PITCH * sizeof(__half)));
   OVN_CUDA(h, cudaMalloc(&t->r16, (size_t)maxp * WF * K4_PITCH * sizeof(__half)));
   OVN_CUDA(h, cudaMemset(t->l16, 0, (size_t)maxp * WF * K4_PITCH * sizeof(__half)));
@@ -1421,8 +1601,8 @@ int tc_pack_weights(ovn_handle* h) {
   OVN_CUDA(h, cudaMemset(t->d_err, 0, sizeof(int)));
   OVN_CUDA(h, cudaMemset(t->o1, 0, (size_t)120 * t->rows_pad * 8 * sizeof(__half)));
   OVN_CUDA(h, cudaMemset(t->x3, 0, (size_t)16 * t->rows_pad * 8 * sizeof(__half)));
-  OVN_CUDA(h, cudaFuncSetAttribute(k_delta_conv1_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem)));
-  OVN_CUDA(h, cudaFuncSetAttribute(k_delta_conv1_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem)));
+  OVN_CUDA(h, cudaFuncSetAttribute(k_delta_conv1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem)));
+  OVN_CUDA(h, cudaFuncSetAttribute(k_conv2_sw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(C2Smem)));
 #define OVN_GEMM_ATTR(E, N, T)                                                                                  \
   OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<E, N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                    (int)sizeof(GSmem<N, T>)))
@@ -1592,34 +1772,20 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query, c
       k_gather_rows_f16<<<(unsigned)((np * per + 255) / 256), 256, 0, s>>>(d_bank, right, np, t->r16);
       OVN_LAUNCH_CHECK(h);
     }
-    const int grid4 = np < h->sm_count ? np : h->sm_count;
-    static const int prod = getenv("OVN_K4_PROD") ? atoi(getenv("OVN_K4_PROD")) : 1;
+    const int64_t units = (int64_t)np * NB;
+    const int grid4 = units < h->sm_count ? (int)units : h->sm_count;
     prof_mark(h, PROF_DELTA, s);
-    if (prod == 1)
-      k_delta_conv1_tc<1><<<grid4, 640, sizeof(K4Smem), s>>>(l16, lidx, t->r16, d_query ? 0 : 1, t->w1p, h->d_b[base + 0],
-                                                             t->o1, t->rows_pad, np, t->d_err);
-    else
-      k_delta_conv1_tc<0><<<grid4, 768, sizeof(K4Smem), s>>>(l16, lidx, t->r16, d_query ? 0 : 1, t->w1p, h->d_b[base + 0],
-                                                             t->o1, t->rows_pad, np, t->d_err);
+    k_delta_conv1_tc<<<grid4, K4_THREADS, sizeof(K4Smem), s>>>(l16, lidx, t->r16, d_query ? 0 : 1, t->w1p, t->o1, np, t->d_err);
     prof_mark(h, PROF_DELTA, s);
     OVN_LAUNCH_CHECK(h);
     const int64_t M = (int64_t)np * PAIR_ROWS;
     const unsigned gx = (unsigned)((M + 511) / 512);
-    GemmArgs a2 = {};
-    a2.A = t->o1; a2.a_pitch = t->rows_pad; a2.copy_plane = t->slab2_plane; a2.copy_shift = t->slab2_shift;
-    a2.n_slabs = 30; a2.Bp = t->w2p; a2.bias = h->d_b[base + 1]; a2.M = M;
-    a2.runs_per_img = 1; a2.in_img_planes = 0; a2.in_run_planes = 0;
-    a2.out_planes = t->x3; a2.out_pitch = t->rows_pad; a2.out_run_planes = 16;
+    const int n_iter2 = (int)((M + 255) / 256);
     prof_mark(h, PROF_CONV2, s);
-    k_gemm_stream_tc<1, 128, 4><<<dim3(gx, 1, 1), G_THREADS, sizeof(GSmem<128, 4>), s>>>(a2, t->d_err);
+    k_conv2_sw_tc<<<n_iter2 < h->sm_count ? n_iter2 : h->sm_count, G_THREADS, sizeof(C2Smem), s>>>(
+        t->o1, t->w2p, t->b2eff, t->x3, t->rows_pad, M, n_iter2, t->d_err);
     prof_mark(h, PROF_CONV2, s);
     OVN_LAUNCH_CHECK(h);
-    GemmArgs a3 = {};
-    a3.A = t->x3; a3.a_pitch = t->rows_pad; a3.copy_plane = t->slab3_plane; a3.copy_shift = t->slab3_shift;
-    a3.n_slabs = 36; a3.Bp = t->w3p; a3.bias = h->d_b[base + 2]; a3.M = M;
-    a3.runs_per_img = 1; a3.in_img_planes = 0; a3.in_run_planes = 0;
-    a3.wd = h->d_w[base + 3]; a3.partial = t->partial; a3.grid_w = NB; a3.valid_w = NB - 2; a3.valid_h = NB - 2;
-    a3.n_total = 256;
     prof_mark(h, PROF_CONV3, s);
     k_conv3_resident_tc<<<dim3(gx, 1, 2), G_THREADS, sizeof(C3Smem), s>>>(t->x3, t->rows_pad, t->w3p, h->d_b[base + 2], M,
                                                                         h->d_w[base + 3], t->partial, t->d_err);
@@ -1660,3 +1826,9 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query, c
 }
 
 }  // namespace ovn
+
+#ifdef OVN_K4_TRACE
+extern "C" int ovn_debug_k4_trace(long long* out_host, long long n_bytes) {
+  return (int)cudaMemcpyFromSymbol(out_host, ovn::g_k4_trace, (size_t)n_bytes);
+}
+#endif

@@ -168,6 +168,15 @@ __device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar, uint32_t parity
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+// Non-blocking probe (mbarrier.test_wait): try_wait may suspend the thread for a system-dependent
+// time when the phase is not complete, which is wrong for a look-ahead probe.
+__device__ __forceinline__ bool mbar_test_addr(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ bool mbar_wait_addr(uint32_t bar, uint32_t parity, long long max_cycles) {
   if (mbar_try_wait_addr(bar, parity)) return true;
   const long long t0 = clock64();
@@ -182,6 +191,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+
+// ---- bulk async copy shared -> global (bulk-group completion) ------------------------------------
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the source shared memory of all committed groups has been read (it may be overwritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;

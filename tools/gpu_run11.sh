@@ -1,18 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-cat > /tmp/leg1.py <<'PY'
-import sys, os
-sys.path.insert(0, os.getcwd())
-import numpy as np, torch
-from overlapnet_b200 import synth
-from overlapnet_b200.engine import Engine
-from oracle import network as N
-MODEL = {'additional_unsymmetric_layer3a': True, 'strides_layer1': [2, 2]}
-eng = Engine(model=MODEL, precision='f16_tc', max_batch_scans=4, max_batch_pairs=16)
-eng.load_weights(N.glorot_weights(4, MODEL, seed=0))
-x = torch.from_numpy(synth.range_like_images(1, 1, 4)).cuda()
-for _ in range(3): eng.leg(x)
-torch.cuda.synchronize()
-PY
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gemm_stream_tc -s 25 -c 1 -o gpurun_out/prof_leg python /tmp/leg1.py > gpurun_out/ncu_leg.log 2>&1
+export OVN_DEBUG_SYNC=1
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_all.log 2>&1
+echo "pytest exit=$?" >> gpurun_out/pytest_all.log
+unset OVN_DEBUG_SYNC
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench3.json 2> gpurun_out/bench3.err
+timeout 300 python tools/time_stages.py f16_tc 1101 > gpurun_out/time_tc.log 2>&1
+timeout 300 python tools/k4_trace.py > gpurun_out/k4_trace.log 2>&1
 echo done
