@@ -831,40 +831,45 @@ done:
 
 // ------------------------------------------------------------------------------------------------
 // k_conv3_resident_tc -- c_conv3 (3x3, 128 -> 256, ReLU) + Flatten + Dense partial sums.
-// The streamed GEMM re-reads the activation tile for each of the 9 taps and both N halves
-// (3.6 GB of L2 traffic per 1101 pairs: L2-bound).  Here the 16 activation planes of a 512-row tile
-// (+64 halo rows) are loaded ONCE (144 KB) and the 3x3 window is applied by the UMMA descriptor
-// itself: tap (dy, dx) is a start-address offset of (dy*24 + dx) rows in the SWIZZLE_NONE layout
-// (16-byte rows at uniform pitch -- probe mode 2).  Only the weights (8 KB per slab) are streamed.
+// The streamed GEMM re-read the activation tile for each of the 9 taps and both N halves (3.6 GB of
+// L2 traffic per 1101 pairs: L2-bound).  Here the 16 activation planes of a 256-row group (+64 halo
+// rows) are loaded ONCE (80 KB) and the 3x3 window is applied by the UMMA descriptor itself: the tap
+// at row shift a*24 + b is a start-address offset in the SWIZZLE_NONE layout (16-byte rows at uniform
+// pitch -- probe mode 2).  Only the weights (8 KB per slab) are streamed.
+// Persistent: a CTA walks row groups; per group two work items (the two 128-channel halves) share
+// the window.  Windows and accumulators (2 tiles x 128 columns per item) are double-buffered, so
+// the window load of the next group and the Dense epilogue of the previous item overlap the MMAs
+// (the one-shot version spent a third of its time in the un-overlapped load and epilogue).
 // ------------------------------------------------------------------------------------------------
-constexpr int C3_ROWS = 512, C3_WIN = 576, C3_PLANES = 16, C3_SLABS = 36, C3_STAGES = 4;
-constexpr int C3_PLANE_BYTES = C3_WIN * 16;             // 9216
+constexpr int C3_ROWS = 256, C3_WIN = 320, C3_PLANES = 16, C3_SLABS = 36, C3_STAGES = 4;
+constexpr int C3_PLANE_BYTES = C3_WIN * 16;             // 5120
+constexpr int C3_WIN_BYTES = C3_PLANES * C3_PLANE_BYTES;   // 81920
 constexpr int C3_B_BYTES = 4 * 128 * 16;                // 8192
 
 struct C3Smem {
-  uint8_t A[C3_PLANES][C3_PLANE_BYTES];
+  uint8_t A[2][C3_WIN_BYTES];
   uint8_t B[C3_STAGES][C3_B_BYTES];
-  float bias[128];
-  uint64_t a_full, full[C3_STAGES], empty[C3_STAGES], d_full;
+  float bias[256];
+  uint64_t a_full[2], a_empty[2], full[C3_STAGES], empty[C3_STAGES], d_full[2], d_empty[2];
   uint32_t tmem_base;
 };
 
 __global__ void __launch_bounds__(G_THREADS, 1)
 k_conv3_resident_tc(const __half* __restrict__ X3, int64_t a_pitch, const __half* __restrict__ Bp,
-                    const float* __restrict__ bias, int64_t M, const float* __restrict__ wd, float* __restrict__ partial,
-                    int* __restrict__ err) {
+                    const float* __restrict__ bias, int64_t M, int n_groups, const float* __restrict__ wd,
+                    float* __restrict__ partial, int* __restrict__ err) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   C3Smem& S = *reinterpret_cast<C3Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t row0 = (int64_t)blockIdx.x * C3_ROWS;
-  const int nh = blockIdx.z;
   if (tid == 0) {
-    mbar_init(&S.a_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&S.a_full[b], 1); mbar_init(&S.a_empty[b], 1);
+      mbar_init(&S.d_full[b], 1); mbar_init(&S.d_empty[b], 4);
+    }
     for (int s = 0; s < C3_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-    mbar_init(&S.d_full, 1);
     mbar_fence_init();
   }
-  if (tid < 128) S.bias[tid] = bias[nh * 128 + tid];
+  S.bias[tid] = bias[tid];                 // G_THREADS == 256 output channels
   if (warp == 2) tmem_alloc(&S.tmem_base, 512);
   fence_before_sync();
   __syncthreads();
@@ -872,16 +877,31 @@ k_conv3_resident_tc(const __half* __restrict__ X3, int64_t a_pitch, const __half
   const uint32_t tmem = S.tmem_base;
 
   if (warp == 0) {
+    // ---- loader: window of group g, then the weight slabs of its two items; the window of the
+    // next group is requested after the first item's slabs so that it lands during the second item
     if (lane == 0) {
-      mbar_arrive_expect_tx(&S.a_full, C3_PLANES * C3_PLANE_BYTES);
-      for (int pl = 0; pl < C3_PLANES; ++pl)
-        bulk_g2s(S.A[pl], X3 + ((size_t)pl * a_pitch + row0) * 8, C3_PLANE_BYTES, &S.a_full);
-      uint32_t s = 0, ph = 0;
-      for (int sl = 0; sl < C3_SLABS; ++sl) {
-        TC_WAIT(&S.empty[s], ph ^ 1, 701);
-        mbar_arrive_expect_tx(&S.full[s], C3_B_BYTES);
-        bulk_g2s(S.B[s], Bp + ((size_t)nh * C3_SLABS + sl) * (C3_B_BYTES / 2), C3_B_BYTES, &S.full[s]);
-        if (++s == C3_STAGES) { s = 0; ph ^= 1; }
+      uint32_t s = 0, ph = 0, gi = 0;
+      auto load_window = [&](int g, uint32_t k) -> bool {
+        const uint32_t ab = k & 1;
+        if (!mbar_wait(&S.a_empty[ab], ((k >> 1) & 1) ^ 1, kWaitCycles)) return false;
+        mbar_arrive_expect_tx(&S.a_full[ab], C3_WIN_BYTES);
+        for (int pl = 0; pl < C3_PLANES; ++pl)
+          bulk_g2s(S.A[ab] + pl * C3_PLANE_BYTES, X3 + ((size_t)pl * a_pitch + (size_t)g * C3_ROWS) * 8, C3_PLANE_BYTES, &S.a_full[ab]);
+        return true;
+      };
+      if ((int)blockIdx.x < n_groups) { if (!load_window(blockIdx.x, 0)) { atomicExch(err, 700); goto done; } }
+      for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++gi) {
+        for (int nh = 0; nh < 2; ++nh) {
+          for (int sl = 0; sl < C3_SLABS; ++sl) {
+            TC_WAIT(&S.empty[s], ph ^ 1, 701);
+            mbar_arrive_expect_tx(&S.full[s], C3_B_BYTES);
+            bulk_g2s(S.B[s], Bp + ((size_t)nh * C3_SLABS + sl) * (C3_B_BYTES / 2), C3_B_BYTES, &S.full[s]);
+            if (++s == C3_STAGES) { s = 0; ph ^= 1; }
+          }
+          if (nh == 0 && g + (int)gridDim.x < n_groups) {
+            if (!load_window(g + gridDim.x, gi + 1)) { atomicExch(err, 700); goto done; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -891,65 +911,88 @@ k_conv3_resident_tc(const __half* __restrict__ X3, int64_t a_pitch, const __half
     const uint64_t bd0 = make_desc_kmajor_noswizzle(smem_u32(S.B[0]), 128 * 16, 128);
     const uint32_t ad_hi = (uint32_t)(ad0 >> 32), ad_lo = (uint32_t)ad0;
     const uint32_t bd_hi = (uint32_t)(bd0 >> 32), bd_lo = (uint32_t)bd0;
-    TC_WAIT(&S.a_full, 0, 702);
-    uint32_t sg = 0, ph = 0;
-#pragma unroll 1
-    for (int tap = 0; tap < 9; ++tap) {
-      const uint32_t shift = (tap / 3) * NB + (tap % 3);                // rows
-#pragma unroll 1
-      for (int gq = 0; gq < 4; ++gq) {                                  // slab = (tap, 32-channel group)
-        TC_WAIT(&S.full[sg], ph, 703);
+    uint32_t sg = 0, ph = 0, gi = 0, item = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++gi) {
+      const uint32_t ab = gi & 1;
+      TC_WAIT(&S.a_full[ab], (gi >> 1) & 1, 702);
+      for (int nh = 0; nh < 2; ++nh, ++item) {
+        const uint32_t db = item & 1;
+        TC_WAIT(&S.d_empty[db], ((item >> 1) & 1) ^ 1, 705);
         fence_after_sync();
-        if (leader) {
-          const uint32_t b_off = (sg * C3_B_BYTES) >> 4;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t shift = (tap / 3) * NB + (tap % 3);                // rows
+#pragma unroll 1
+          for (int gq = 0; gq < 4; ++gq) {                                  // slab = (tap, 32-channel group)
+            TC_WAIT(&S.full[sg], ph, 703);
+            fence_after_sync();
+            if (leader) {
+              const uint32_t b_off = (sg * C3_B_BYTES) >> 4;
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(bd_lo + b_off + ((kk * 2 * (128 * 16)) >> 4));
-            const uint32_t a_k = ad_lo + (((gq * 4 + kk * 2) * C3_PLANE_BYTES + shift * 16) >> 4);
+              for (int kk = 0; kk < 2; ++kk) {
+                const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(bd_lo + b_off + ((kk * 2 * (128 * 16)) >> 4));
+                const uint32_t a_k = ad_lo + ((ab * C3_WIN_BYTES + (gq * 4 + kk * 2) * C3_PLANE_BYTES + shift * 16) >> 4);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const uint64_t ad = ((uint64_t)ad_hi << 32) | (uint64_t)(a_k + ((t * 128 * 16) >> 4));
-              mma_ss(tmem + t * 128, ad, bd, idesc, (tap | gq | kk) != 0);
+                for (int t = 0; t < 2; ++t) {
+                  const uint64_t ad = ((uint64_t)ad_hi << 32) | (uint64_t)(a_k + ((t * 128 * 16) >> 4));
+                  mma_ss(tmem + db * 256 + t * 128, ad, bd, idesc, (tap | gq | kk) != 0);
+                }
+              }
+              commit(&S.empty[sg]);
             }
+            __syncwarp();
+            if (++sg == C3_STAGES) { sg = 0; ph ^= 1; }
           }
-          commit(&S.empty[sg]);
+        }
+        if (leader) {
+          commit(&S.d_full[db]);
+          if (nh == 1) commit(&S.a_empty[ab]);
         }
         __syncwarp();
-        if (++sg == C3_STAGES) { sg = 0; ph ^= 1; }
       }
     }
-    if (leader) commit(&S.d_full);
-    __syncwarp();
   } else if (warp >= 4) {
     const int q = warp & 3;
-    TC_WAIT(&S.d_full, 0, 704);
-    fence_after_sync();
+    uint32_t item = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+      for (int nh = 0; nh < 2; ++nh, ++item) {
+        const uint32_t db = item & 1;
+        TC_WAIT(&S.d_full[db], (item >> 1) & 1, 704);
+        fence_after_sync();
 #pragma unroll 1
-    for (int t = 0; t < 4; ++t) {
-      const int64_t r = row0 + t * 128 + q * 32 + lane;
-      const int rem = (int)(r % PAIR_ROWS);
-      const int yy = rem / NB, xx = rem - yy * NB;
-      const bool valid = (r < M) && (yy < NB - 2) && (xx < NB - 2);
-      // rows are (pair, jb, ib): yy = jb, xx = ib; Flatten order of the reference is (ib, jb, channel)
-      const float* wrow = wd + ((size_t)(valid ? (xx * (NB - 2) + yy) : 0) * 256 + nh * 128);
-      float acc = 0.f;
+        for (int t = 0; t < 2; ++t) {
+          const int64_t r = (int64_t)g * C3_ROWS + t * 128 + q * 32 + lane;
+          const int rem = (int)(r % PAIR_ROWS);
+          const int yy = rem / NB, xx = rem - yy * NB;
+          const bool valid = (r < M) && (yy < NB - 2) && (xx < NB - 2);
+          // rows are (pair, jb, ib): yy = jb, xx = ib; Flatten order of the reference is (ib, jb, channel)
+          const float* wrow = wd + ((size_t)(valid ? (xx * (NB - 2) + yy) : 0) * 256 + nh * 128);
+          float acc = 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * 128 + c0, v);
-        tmem_ld_wait();
-        if (valid) {
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + db * 256 + t * 128 + c0, v);
+            float4 w[8];
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + c0) + j4);
-            acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 0]) + S.bias[c0 + j4 * 4 + 0], 0.f), w.x, acc);
-            acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 1]) + S.bias[c0 + j4 * 4 + 1], 0.f), w.y, acc);
-            acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 2]) + S.bias[c0 + j4 * 4 + 2], 0.f), w.z, acc);
-            acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 3]) + S.bias[c0 + j4 * 4 + 3], 0.f), w.w, acc);
+            for (int j4 = 0; j4 < 8; ++j4) w[j4] = __ldg(reinterpret_cast<const float4*>(wrow + c0) + j4);
+            tmem_ld_wait();
+            if (t == 1 && c0 == 96) {          // the last accumulator columns of this item are in registers
+              fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&S.d_empty[db]);
+            }
+            const float* bs = S.bias + nh * 128 + c0;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 0]) + bs[j4 * 4 + 0], 0.f), w[j4].x, acc);
+              acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 1]) + bs[j4 * 4 + 1], 0.f), w[j4].y, acc);
+              acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 2]) + bs[j4 * 4 + 2], 0.f), w[j4].z, acc);
+              acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 3]) + bs[j4 * 4 + 3], 0.f), w[j4].w, acc);
+            }
           }
+          if (r < M) partial[r * 2 + nh] = valid ? acc : 0.f;
         }
       }
-      if (r < M) partial[r * 2 + nh] = valid ? acc : 0.f;
     }
   }
 done:
@@ -1779,7 +1822,6 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query, c
     prof_mark(h, PROF_DELTA, s);
     OVN_LAUNCH_CHECK(h);
     const int64_t M = (int64_t)np * PAIR_ROWS;
-    const unsigned gx = (unsigned)((M + 511) / 512);
     const int n_iter2 = (int)((M + 255) / 256);
     prof_mark(h, PROF_CONV2, s);
     k_conv2_sw_tc<<<n_iter2 < h->sm_count ? n_iter2 : h->sm_count, G_THREADS, sizeof(C2Smem), s>>>(
@@ -1787,8 +1829,8 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query, c
     prof_mark(h, PROF_CONV2, s);
     OVN_LAUNCH_CHECK(h);
     prof_mark(h, PROF_CONV3, s);
-    k_conv3_resident_tc<<<dim3(gx, 1, 2), G_THREADS, sizeof(C3Smem), s>>>(t->x3, t->rows_pad, t->w3p, h->d_b[base + 2], M,
-                                                                        h->d_w[base + 3], t->partial, t->d_err);
+    k_conv3_resident_tc<<<n_iter2 < h->sm_count ? n_iter2 : h->sm_count, G_THREADS, sizeof(C3Smem), s>>>(
+        t->x3, t->rows_pad, t->w3p, h->d_b[base + 2], M, n_iter2, h->d_w[base + 3], t->partial, t->d_err);
     prof_mark(h, PROF_CONV3, s);
     OVN_LAUNCH_CHECK(h);
     k_dense_finalize<<<np, 256, 0, s>>>(t->partial, h->d_b[base + 3], PAIR_ROWS, d_overlap + p0);
