@@ -1177,7 +1177,7 @@ done:
 // 128 x 192 tile from TMEM and rotates a running accumulator across lanes (bin(lane, col+1) ==
 // bin(lane-1, col)), flushing one finished bin per column.
 // ------------------------------------------------------------------------------------------------
-constexpr int C6_THREADS = 256;
+constexpr int C6_THREADS = 384;            // warps 0-2: loader, MMA issuer, TMEM owner; warps 4-11: epilogue (2 per TMEM lane quarter)
 constexpr int C6_STAGES = 3;
 constexpr int C6_STAGE_BYTES = 32768;            // [hi,lo][8 planes][128 rows][8] fp16
 constexpr int C6_R_BYTES = 98304;                // [hi,lo][16 planes][192 rows][8] fp16
@@ -1187,7 +1187,7 @@ constexpr int C6_VOL_R_BYTES = 2 * C6_R_BYTES;
 struct C6Smem {
   uint8_t R[C6_R_BYTES];
   uint8_t A[C6_STAGES][C6_STAGE_BYTES];
-  float corr[4][WF];
+  float corr[8][WF];
   uint64_t full[C6_STAGES], empty[C6_STAGES], d_full[2], d_empty[2], r_full, r_empty, epi;
   uint32_t tmem_base;
 };
@@ -1278,8 +1278,8 @@ k_corr_tc(const __half* __restrict__ Lc, const int32_t* __restrict__ l_idx, cons
 
   if (tid == 0) {
     for (int s = 0; s < C6_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&S.d_full[b], 1); mbar_init(&S.d_empty[b], 4); }
-    mbar_init(&S.r_full, 1); mbar_init(&S.r_empty, 1); mbar_init(&S.epi, 4);
+    for (int b = 0; b < 2; ++b) { mbar_init(&S.d_full[b], 1); mbar_init(&S.d_empty[b], 8); }
+    mbar_init(&S.r_full, 1); mbar_init(&S.r_empty, 1); mbar_init(&S.epi, 8);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(&S.tmem_base, 512);
@@ -1357,9 +1357,17 @@ k_corr_tc(const __half* __restrict__ Lc, const int32_t* __restrict__ l_idx, cons
       }
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;
-    float* my = S.corr[q];
-    uint32_t tileit = 0, rz = 0;      // rz: rendezvous count of the 4 epilogue warps (bounded mbarrier, never bar.sync)
+    // ---- epilogue: corr[(i - j - 180) mod 360] += G[i][j], i.e. sums along the diagonals of the tile.
+    // Lane l holds row i0 + l, registers v[cc] the columns j0 + cc of a 32-column chunk; element
+    // (l, cc) lies on diagonal d = l - cc.  A first version walked the columns with a rotating
+    // accumulator (two dependent shuffles per column: 60 clk x 192 columns per tile, 3x the MMA time).
+    // Now: (1) each lane rotates its registers by its lane index (5-stage barrel shifter of selects),
+    // which puts diagonal d == m (mod 32) into register m; (2) two masked reduce-scatters (31 shuffles
+    // each, all independent within a stage) leave in lane m the sums of diagonals m and m - 32;
+    // (3) one shared-memory add per lane and chunk, the m - 32 part carried into the next chunk.
+    const int q = warp & 3, half = (warp - 4) >> 2;        // this warp's chunks: half*3 .. half*3 + 2
+    float* my = S.corr[warp - 4];
+    uint32_t tileit = 0, rz = 0;      // rz: rendezvous count of the 8 epilogue warps (bounded mbarrier, never bar.sync)
     for (int p = cta; p < n_pairs; p += n_cta) {
       for (int k = lane; k < WF; k += 32) my[k] = 0.f;
       __syncwarp();
@@ -1367,50 +1375,68 @@ k_corr_tc(const __half* __restrict__ Lc, const int32_t* __restrict__ l_idx, cons
         const uint32_t buf = tileit & 1;
         TC_WAIT(&S.d_full[buf], (tileit >> 1) & 1, 607);
         fence_after_sync();
-        // bin(lane, col) = (i - j - 180) mod 360 with i = t*128 + q*32 + lane, j = h*192 + col
-        const int b31 = t * 128 + q * 32 + 31 - h * 192 - 180;     // bin of lane 31 at col 0 (before wrap)
-        float acc = 0.f, pend = 0.f;
+        float carry = 0.f;
+        int b0 = 0;
 #pragma unroll 1
-        for (int ch = 0; ch < 6; ++ch) {
+        for (int c3 = 0; c3 < 3; ++c3) {
+          const int ch = half * 3 + c3;
           uint32_t v[32];
           tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + buf * 192 + ch * 32, v);
           tmem_ld_wait();
-          if (ch == 5) {                     // all of this tile is in registers / consumed: release the buffer
+          if (c3 == 2) {                     // this warp's part of the tile is in registers: release the buffer
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.d_empty[buf]);
           }
+          // (1) u[m] = v[(lane - m) & 31]: reverse (free renaming), then rotate right by `lane`
+          float u[32];
 #pragma unroll
-          for (int cc = 0; cc < 32; ++cc) {
-            if (ch > 0 || cc > 0) {
-              // retire lane 31's accumulator (the bin that leaves this warp) into lane (col-1)&31's pend
-              const float out = __shfl_sync(0xffffffffu, acc, 31);
-              if (lane == ((cc + 31) & 31)) pend = out;
-              if (cc == 0) {
-                // cols (ch-1)*32 .. ch*32-1 retired: lane l holds the bin of lane 31 at col (ch-1)*32 + l
-                const int bin = wrap360(b31 - ((ch - 1) * 32 + lane));
-                my[bin] += pend;
-                __syncwarp();
-              }
-              acc = __shfl_up_sync(0xffffffffu, acc, 1);
-              if (lane == 0) acc = 0.f;
-            }
-            acc += __uint_as_float(v[cc]);
+          for (int m = 0; m < 32; ++m) u[m] = __uint_as_float(v[(32 - m) & 31]);
+#pragma unroll
+          for (int b = 0; b < 5; ++b) {
+            const bool on = (lane >> b) & 1;
+            float w[32];
+#pragma unroll
+            for (int m = 0; m < 32; ++m) w[m] = on ? u[(m - (1 << b)) & 31] : u[m];
+#pragma unroll
+            for (int m = 0; m < 32; ++m) u[m] = w[m];
           }
+          // (2) diagonal m (lanes >= m) and diagonal m - 32 (lanes < m), reduce-scattered to lane m
+          float x[32], y[32];
+#pragma unroll
+          for (int m = 0; m < 32; ++m) {
+            const bool ge = lane >= m;
+            x[m] = ge ? u[m] : 0.f;
+            y[m] = ge ? 0.f : u[m];
+          }
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int k = 0; k < o; ++k) {
+              const float sx = up ? x[k] : x[k + o], kx = up ? x[k + o] : x[k];
+              const float sy = up ? y[k] : y[k + o], ky = up ? y[k + o] : y[k];
+              x[k] = kx + __shfl_xor_sync(0xffffffffu, sx, o);
+              y[k] = ky + __shfl_xor_sync(0xffffffffu, sy, o);
+            }
+          }
+          // (3) bin of (lane 0, column 0 of the chunk), before wrap
+          b0 = t * 128 + q * 32 - h * 192 - ch * 32 - 180;
+          my[wrap360(b0 + lane)] += x[0] + carry;
+          carry = y[0];
         }
-        // tail: cols 160..190 retired into lanes 0..30 of pend; col 191's accumulators still in acc
-        if (lane < 31) my[wrap360(b31 - (160 + lane))] += pend;
-        __syncwarp();
-        my[wrap360(b31 - 31 + lane - 191)] += acc;
-        __syncwarp();
+        my[wrap360(b0 - 32 + lane)] += carry;
+        __syncwarp();                        // the next tile's bins belong to other lanes
       }
-      // combine the four warps' private arrays in a fixed order (bit-reproducible)
+      // combine the eight warps' private arrays in a fixed order (bit-reproducible)
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.epi);
       TC_WAIT(&S.epi, rz & 1, 608);
       ++rz;
-      for (int k = tid - 128; k < WF; k += 128)
-        corr_part[((size_t)p * 2 + h) * WF + k] = ((S.corr[0][k] + S.corr[1][k]) + S.corr[2][k]) + S.corr[3][k];
+      for (int k = tid - 128; k < WF; k += 256)
+        corr_part[((size_t)p * 2 + h) * WF + k] =
+            (((S.corr[0][k] + S.corr[1][k]) + (S.corr[2][k] + S.corr[3][k])) +
+             ((S.corr[4][k] + S.corr[5][k]) + (S.corr[6][k] + S.corr[7][k])));
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.epi);
       TC_WAIT(&S.epi, rz & 1, 609);
@@ -1458,6 +1484,71 @@ k_dense_finalize(const float* __restrict__ partial, const float* __restrict__ bd
     __syncthreads();
   }
   if (threadIdx.x == 0) overlap[p] = 1.0f / (1.0f + expf(-(red[0] + bd[0])));
+}
+
+// Leg layer 1 (5x15 stride (2,2), C_in = 4..25 -> 16, ReLU) straight from the fp32 NHWC input
+// image to the hi/lo fp16 planes layer 2 reads.  K = kh*kw*C_in is only 300 for the geometric cues
+// and N = 16: as a 64x64-tiled SIMT GEMM this took 61 us of a 245 us single-scan leg.  One thread
+// per (output pixel, 8 output channels); weights live in shared memory and are read by broadcast.
+template <bool CIN4>
+__global__ void __launch_bounds__(256)
+k_leg_layer1_direct(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                    int n, int H_in, int W_in, int cin, int kh, int kw, int sh, int sw, int H_out, int W_out, int cout,
+                    int relu, __half* __restrict__ out) {
+  extern __shared__ __align__(16) float w_s[];              // [kh*kw*cin][cout]
+  for (int i = threadIdx.x; i < kh * kw * cin * cout; i += blockDim.x) w_s[i] = w[i];
+  __syncthreads();
+  const int C8 = cout / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (img, y, c8, x)
+  if (idx >= (int64_t)n * H_out * C8 * W_out) return;
+  const int xo = (int)(idx % W_out);
+  int64_t r = idx / W_out;
+  const int g = (int)(r % C8); r /= C8;                                   // r = img*H_out + y
+  const int y = (int)(r % H_out);
+  const int64_t img = r / H_out;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = bias[g * 8 + e];
+  const float* base = x + ((img * H_in + (int64_t)y * sh) * W_in + (int64_t)xo * sw) * cin;
+  for (int dh = 0; dh < kh; ++dh) {
+    for (int dw = 0; dw < kw; ++dw) {
+      const float* px = base + ((int64_t)dh * W_in + dw) * cin;
+      const float* pw = w_s + (size_t)((dh * kw + dw) * cin) * cout + g * 8;
+      if (CIN4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(px));
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 w0 = *reinterpret_cast<const float4*>(pw + c * cout);
+          const float4 w1 = *reinterpret_cast<const float4*>(pw + c * cout + 4);
+          acc[0] = fmaf(vv[c], w0.x, acc[0]); acc[1] = fmaf(vv[c], w0.y, acc[1]);
+          acc[2] = fmaf(vv[c], w0.z, acc[2]); acc[3] = fmaf(vv[c], w0.w, acc[3]);
+          acc[4] = fmaf(vv[c], w1.x, acc[4]); acc[5] = fmaf(vv[c], w1.y, acc[5]);
+          acc[6] = fmaf(vv[c], w1.z, acc[6]); acc[7] = fmaf(vv[c], w1.w, acc[7]);
+        }
+      } else {
+        for (int c = 0; c < cin; ++c) {
+          const float vc = __ldg(px + c);
+          const float4 w0 = *reinterpret_cast<const float4*>(pw + c * cout);
+          const float4 w1 = *reinterpret_cast<const float4*>(pw + c * cout + 4);
+          acc[0] = fmaf(vc, w0.x, acc[0]); acc[1] = fmaf(vc, w0.y, acc[1]);
+          acc[2] = fmaf(vc, w0.z, acc[2]); acc[3] = fmaf(vc, w0.w, acc[3]);
+          acc[4] = fmaf(vc, w1.x, acc[4]); acc[5] = fmaf(vc, w1.y, acc[5]);
+          acc[6] = fmaf(vc, w1.z, acc[6]); acc[7] = fmaf(vc, w1.w, acc[7]);
+        }
+      }
+    }
+  }
+  __half hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float v = relu ? fmaxf(acc[e], 0.f) : acc[e];
+    hi[e] = __float2half_rn(v);
+    lo[e] = __float2half_rn(v - __half2float(hi[e]));
+  }
+  const int64_t plane_hi = r * (2 * C8) + g;                               // [img][y][hi,lo][c8][x][8]
+  *reinterpret_cast<uint4*>(out + ((size_t)plane_hi * W_out + xo) * 8) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(out + ((size_t)(plane_hi + C8) * W_out + xo) * 8) = *reinterpret_cast<const uint4*>(lo);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1653,6 +1744,8 @@ int tc_pack_weights(ovn_handle* h) {
   OVN_CUDA(h, cudaFuncSetAttribute(k_conv3_resident_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(C3Smem)));
   OVN_GEMM_ATTR(4, 64, 4); OVN_GEMM_ATTR(4, 128, 4); OVN_GEMM_ATTR(3, 128, 4);
   OVN_GEMM_ATTR(4, 64, 1); OVN_GEMM_ATTR(3, 64, 1);
+  OVN_CUDA(h, cudaFuncSetAttribute(k_leg_layer1_direct<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  OVN_CUDA(h, cudaFuncSetAttribute(k_leg_layer1_direct<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   OVN_CUDA(h, cudaFuncSetAttribute(k_leg_resident_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LRSmem)));
   OVN_CUDA(h, cudaFuncSetAttribute(k_leg_resident_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LRSmem)));
 #undef OVN_GEMM_ATTR
@@ -1689,13 +1782,24 @@ int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cuda
   TcState* t = h->tc;
   if (!t) OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "tensor-core weights not packed");
   prof_mark(h, PROF_LEG, s);
-  int rc = leg_layer_fp32(h, 0, d_input, h->d_act[0], n, s);
-  if (rc != OVN_OK) return rc;
   {
     const ConvSpec& L = h->leg[0];
     const int64_t chunks = (int64_t)n * L.h_out * (L.cout / 8) * L.w_out;
-    k_nhwc_to_planes<<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(h->d_act[0], chunks, L.h_out, L.w_out,
-                                                                     L.cout / 8, t->actp[0]);
+    const size_t w_bytes = (size_t)L.kh * L.kw * L.cin * L.cout * sizeof(float);
+    if (w_bytes <= 200 * 1024 && L.cout % 8 == 0) {
+      const unsigned grid = (unsigned)((chunks + 255) / 256);
+      if (L.cin == 4)
+        k_leg_layer1_direct<true><<<grid, 256, w_bytes, s>>>(d_input, h->d_w[0], h->d_b[0], n, L.h_in, L.w_in, L.cin, L.kh, L.kw,
+                                                            L.sh, L.sw, L.h_out, L.w_out, L.cout, L.relu, t->actp[0]);
+      else
+        k_leg_layer1_direct<false><<<grid, 256, w_bytes, s>>>(d_input, h->d_w[0], h->d_b[0], n, L.h_in, L.w_in, L.cin, L.kh, L.kw,
+                                                             L.sh, L.sw, L.h_out, L.w_out, L.cout, L.relu, t->actp[0]);
+    } else {
+      int rc = leg_layer_fp32(h, 0, d_input, h->d_act[0], n, s);
+      if (rc != OVN_OK) return rc;
+      k_nhwc_to_planes<<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(h->d_act[0], chunks, L.h_out, L.w_out,
+                                                                       L.cout / 8, t->actp[0]);
+    }
     OVN_LAUNCH_CHECK(h);
   }
   int cur = 0;
