@@ -313,7 +313,7 @@ def main():
         'roofline': {'kernel': 'k_delta_conv1_tc' if args.precision == 'f16_tc' else 'k_simt_gemm<DeltaOperand>',
                      'bound': 'tensor', 'achieved': ach, 'peak': tflops_peak, 'unit': 'TFLOP/s',
                      'frac': (ach / tflops_peak) if ach else None, 'traffic': traffic,
-                     'traffic_note': 'DRAM bytes per launch from the committed ncu capture (profiles/r1_ncu_summary.txt); algorithmic bytes 1.32e9',
+                     'traffic_note': 'DRAM bytes per launch from the committed ncu capture (profiles/r1_ncu_summary_v2.txt); algorithmic bytes 1.32e9 (108 MB of LEFT volumes + 1.21 GB of o1)',
                      'peak_source': peak_src,
                      'flop_per_launch': N_CAND * FLOP_DELTA_CONV1, 'avg_launch_ms': k_ms / max(k_n, 1),
                      'share_of_step': shares},

@@ -1,28 +1,28 @@
 // network_tc.cu -- tensor-core (tcgen05 / TMEM / bulk-async-copy) path of the two heads.
 //
 // Replaces: DeltaLayer + c_conv1 (generateNet.py:15-61,96-100)      -> k_delta_conv1_tc
-//           c_conv2, c_conv3 (+ReLU) (generateNet.py:102-110)       -> k_gemm_stream_tc
-//           Flatten + Dense(1, sigmoid) (generateNet.py:112-114)    -> fused epilogue + k_dense_finalize
+//           c_conv2 (+ReLU) (generateNet.py:102-105)                -> k_conv2_sw_tc
+//           c_conv3 (+ReLU), Flatten + Dense(1, sigmoid) (:107-114) -> k_conv3_resident_tc + k_dense_finalize
+//           NormalizedCorrelation2D + argmax (:117-143, infer.py)   -> k_corr_tc + k_corr_finalize
+//           leg Conv2D stack (generateNet.py:149-230)               -> k_leg_layer1_direct, k_leg_resident_tc,
+//                                                                      k_gemm_stream_tc (batched)
 //
 // k_delta_conv1_tc (the kernel that decides scan-pairs/s; 83 % of the FLOPs of a pair)
-//   GEMM view per pair:  o1[(i, jb), o] = b1[o] + sum_{dj<15, c<128} |L[i,c] - R[15 jb + dj, c]| W1[dj, c, o]
+//   GEMM view per pair:  o1[(i, jb), o] = sum_{dj<15, c<128} |L[i,c] - R[15 jb + dj, c]| W1[dj, c, o]
 //   M = 360 x 24, N = 64, K = 1920.  The A operand (66 MB per pair in the reference) is never
-//   materialised: 8 producer warps synthesise |l - r| as packed fp16 straight into TENSOR MEMORY
-//   (tcgen05.st), one warp's single thread issues tcgen05.mma in TS mode (A from TMEM, B = W1
+//   materialised: 12 producer warps synthesise |l - r| as packed fp16 straight into TENSOR MEMORY
+//   (tcgen05.st), one warp's elected lane issues tcgen05.mma in TS mode (A from TMEM, B = W1
 //   slice from shared memory), accumulators (3 row tiles x 64 fp32 columns) live in TMEM.
-//   Mapping: TMEM lane = LEFT row i (3 tiles: i0 = 0, 128, 256), one CTA works through jb = 0..23
-//   of a pair; a thread keeps its three LEFT rows' current 16 channels in registers and reads the
-//   RIGHT row by broadcast LDS, so each synthesised element costs ~1 ALU instruction.
-//   W1 (245 KB fp16) does not fit in shared memory next to L and R: it is streamed per stage
-//   (4 KB slices, cp.async.bulk + mbarrier) through a 6-deep ring that is recycled by
-//   tcgen05.commit.  Roofline: tensor pipe (co-limited by operand synthesis).
+//   Mapping: TMEM lane = LEFT row i (3 tiles: i0 = 0, 128, 256); a thread keeps its three LEFT
+//   rows' current 32 channels in registers and reads the RIGHT row by broadcast LDS, so each
+//   synthesised element costs ~1 ALU instruction.  W1 (245 KB fp16) is streamed in 24 KB groups
+//   (cp.async.bulk + mbarrier) through a ring recycled by tcgen05.commit.
+//   Roofline: tensor pipe (co-limited by operand synthesis).
 //
-// k_gemm_stream_tc
-//   D[512 rows x 128] += sum over K-slabs of A_slab[512 x 32] * B_slab[128 x 32]^T with both
-//   operands streamed global -> shared by cp.async.bulk in the "C8-interleaved" layout
-//   [channel/8][row][8] (16-byte core-matrix rows at uniform pitch, SWIZZLE_NONE descriptors).
-//   A per-slab row shift turns the same kernel into the 3x3 convolution c_conv3 (implicit
-//   im2col at the copy level: the window shift is just a different source row).
+// SS-mode GEMM kernels: operands in shared memory either as C8-interleaved planes
+//   [channel/8][row][8] (16-byte core-matrix rows at uniform pitch, SWIZZLE_NONE descriptors; a row
+//   shift of the descriptor start address is a convolution tap) or as SWIZZLE_128B tiles
+//   [128 rows][64 K] (k_conv2_sw_tc: o1 is written by k_delta_conv1_tc already in that image).
 #include "common.cuh"
 #include "umma.cuh"
 
