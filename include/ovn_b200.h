@@ -127,6 +127,24 @@ int ovn_semantic_batch(ovn_handle* h, const int32_t* d_idx, const float* d_probs
                        const int64_t* d_offsets, int32_t n_scans, int32_t n_classes,
                        float* d_out /* [n][H][W][n_classes] */, void* stream);
 
+/* ---- ground-truth generator (com_overlap_yaw.py:10-68) ------------------------- */
+/* Float32 range images [n][H][W] of scans moved into the current frame: every point (x, y, z, 1)
+ * is multiplied, in float64, by d_pose_ref[scan] and then by d_pose_cur_inv (row-major 4x4, either
+ * may be NULL = identity; com_overlap_yaw.py:39-40) and projected by range_projection evaluated in
+ * FLOAT64 (the reference's load_vertex builds a float64 array, utils.py:218-231; bins utils.py:75-104),
+ * nearest point per pixel, depth rounded to float32 on store, -1 where empty (utils.py:120,129).
+ * max_range < 0 selects the handle's configured max_range. */
+int ovn_gt_range_batch(ovn_handle* h, const float* d_points, const int64_t* d_offsets, int32_t n_scans,
+                       int64_t n_points_total, const double* d_pose_ref /* [n][16] */,
+                       const double* d_pose_cur_inv /* [16] */, float max_range,
+                       float* d_range /* [n][H][W] */, void* stream);
+
+/* d_counts[b] = #{pixels: ref_b > 0 and |ref_b - cur| < 1} for b < n_scans (com_overlap_yaw.py:44-45,
+ * float32 arithmetic); d_counts[n_scans] = #{cur > 0} = the reference's valid_num (:31-32). */
+int ovn_gt_overlap_count(ovn_handle* h, const float* d_ref_ranges /* [n][H][W] */,
+                         const float* d_cur_range /* [H][W] */, int32_t n_scans,
+                         int32_t* d_counts /* [n_scans + 1] */, void* stream);
+
 /* ---- stage 1d: fused raw cloud -> packed network input ------------------------------------- */
 /* Projection + normals + channel packing (ImagePairOverlapOrientationSequence.py:130-207) in one
  * pass; d_probs may be NULL when n_prob_channels == 0.  d_input: [n][H][W][C] float32. */

@@ -20,6 +20,10 @@ network.py     torch-CPU restatement of the leg (``generateNet.py:119-219``), th
                reference activation exists to compare with.  It is pinned only by the
                reference's own known-answer statements (RangePadding2D.py:5 KAT, the analytic
                shift KAT of the correlation head) and by an independent naive loop restatement.
+gt.py          NumPy restatement of the ground-truth generator ``src/utils/com_overlap_yaw.py:10-68``
+               (float64 range projection, float32 image compare, yaw bin).  PARITY PINNED: bit-exact
+               against the reference's own ``com_overlap_yaw`` run in the build container
+               (tools/make_golden_gt.py -> tests/golden/gt_overlap_yaw.npz).
 infer_ref.py   restatement of the ``Infer`` class call semantics (``infer.py:22-265``) on top of
                projection.py + network.py.
 """

@@ -342,6 +342,24 @@ int ovn_semantic_batch(ovn_handle* h, const int32_t* d_idx, const float* d_probs
   return semantic_batch(h, d_idx, d_probs, d_offsets, n_scans, n_classes, d_out, (cudaStream_t)stream);
 }
 
+int ovn_gt_range_batch(ovn_handle* h, const float* d_points, const int64_t* d_offsets, int32_t n_scans,
+                       int64_t n_total, const double* d_pose_ref, const double* d_pose_cur_inv, float max_range,
+                       float* d_range, void* stream) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  REQUIRE(h, n_scans >= 0 && n_total >= 0, "negative size");
+  REQUIRE(h, n_scans == 0 || (d_offsets && d_range && (d_points || n_total == 0)), "NULL pointer");
+  return gt_range_batch(h, d_points, d_offsets, n_scans, n_total, d_pose_ref, d_pose_cur_inv, max_range, d_range,
+                        (cudaStream_t)stream);
+}
+
+int ovn_gt_overlap_count(ovn_handle* h, const float* d_ref_ranges, const float* d_cur_range, int32_t n_scans,
+                         int32_t* d_counts, void* stream) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  REQUIRE(h, n_scans >= 0, "negative size");
+  REQUIRE(h, d_cur_range && d_counts && (n_scans == 0 || d_ref_ranges), "NULL pointer");
+  return gt_overlap_count(h, d_ref_ranges, d_cur_range, n_scans, d_counts, (cudaStream_t)stream);
+}
+
 int ovn_preprocess_batch(ovn_handle* h, const float* d_points, const int64_t* d_offsets, int32_t n_scans,
                          int64_t n_total, const float* d_probs, float* d_input, void* stream) {
   if (!h) return OVN_ERR_INVALID_ARG;

@@ -147,6 +147,31 @@ class Engine:
           self._stream()), 'ovn_project_batch')
     return out
 
+  def gt_range(self, batch, pose_ref=None, pose_cur_inv=None, max_range=-1.0):
+    """ovn_gt_range_batch: float32 range images of the scans of a CloudBatch after the two float64
+    pose products of com_overlap_yaw.py:39-40 (``pose_ref``: (n,4,4) float64 or None, ``pose_cur_inv``:
+    (4,4) float64 or None), projected in float64 like the reference's GT generator."""
+    n = batch.n
+    dev = self.device
+    out = torch.empty((n, self.H, self.W), dtype=torch.float32, device=dev)
+    pr = None if pose_ref is None else torch.as_tensor(pose_ref, dtype=torch.float64).reshape(n, 16).to(dev).contiguous()
+    pc = None if pose_cur_inv is None else torch.as_tensor(pose_cur_inv, dtype=torch.float64).reshape(16).to(dev).contiguous()
+    L = lib()
+    for s0, s1, p0, p1, pts, offs in self._chunks(batch):
+      check(self._h, L.ovn_gt_range_batch(
+          self._h, _ptr(pts), _ptr(offs), s1 - s0, p1 - p0, _ptr(pr[s0:s1]) if pr is not None else None, _ptr(pc),
+          float(max_range), _ptr(out[s0:s1]), self._stream()), 'ovn_gt_range_batch')
+    return out
+
+  def gt_overlap_count(self, ref_ranges, cur_range):
+    """ovn_gt_overlap_count: int32 [n + 1]: per reference image the number of pixels with ref > 0 and
+    |ref - cur| < 1 (com_overlap_yaw.py:44-45); last entry = number of valid pixels of ``cur_range``."""
+    n = ref_ranges.shape[0]
+    counts = torch.empty((n + 1,), dtype=torch.int32, device=self.device)
+    check(self._h, lib().ovn_gt_overlap_count(self._h, _ptr(ref_ranges), _ptr(cur_range), n, _ptr(counts),
+                                             self._stream()), 'ovn_gt_overlap_count')
+    return counts
+
   def normals(self, rng, vertex):
     n = rng.shape[0]
     out = torch.empty((n, self.H, self.W, 3), dtype=torch.float32, device=self.device)
