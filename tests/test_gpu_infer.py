@@ -145,3 +145,30 @@ def test_infer_raw_cloud_extension(dataset, tmp_path):
   ov_raw, yaw_raw = inf.infer_one_raw(str(tmp_path / '000000.bin'), str(tmp_path / '000001.bin'))
   ov_npy, yaw_npy = inf.infer_one('000000.bin', '000001.bin')
   assert np.array_equal(ov_raw, ov_npy) and np.array_equal(yaw_raw, yaw_npy)
+
+
+def test_evaluation_flow_matches_reference_semantics(dataset, tmp_path):
+  """testing.py:207-352 on the GPU path: every distinct scan encoded once, LEFT = imgf1, RIGHT =
+  imgf2, statistics and validation_results.npz -- against the oracle run pair by pair."""
+  from overlapnet_b200 import evaluate as E
+  cfg, w = dataset
+  cfg = copy.deepcopy(cfg)
+  gt = np.array([[0, 1, 0.93, 155.0], [1, 0, 0.93, 205.0], [2, 0, 0.80, 230.0], [3, 1, 0.05, 17.0], [0, 0, 1.0, 180.0]])
+  (tmp_path / '07' / 'ground_truth').mkdir(parents=True)
+  seq = np.empty((len(gt), 2), dtype=object); seq[:] = '07'
+  np.savez_compressed(str(tmp_path / '07' / 'ground_truth' / 'ground_truth_overlap_yaw.npz'), overlaps=gt, seq=seq)
+  run_cfg = dict(cfg, testing_seqs='07', imgpath=cfg['data_root_folder'], data_root_folder=str(tmp_path),
+                 experiments_path=str(tmp_path), testname='exp', no_test_pairs=10 ** 9)
+  del run_cfg['infer_seqs']
+  m, stats = E.run_testing(run_cfg, precision='fp32')
+  saved = np.load(str(tmp_path / 'exp' / 'validation_results.npz'))['arr_0']
+  assert np.array_equal(saved, m) and m.shape == (5, 4)
+  assert np.array_equal(m[:, :2], gt[:, :2])
+  ref = InferRef(copy.deepcopy(cfg), w)
+  for row in m:
+    a, b = '%06d.bin' % int(row[0]), '%06d.bin' % int(row[1])
+    ov_r, yaw_r, corr_r = ref.infer_one(b, a)               # infer_one: LEFT = file2, RIGHT = file1
+    assert abs(row[2] - float(ov_r[0])) <= 1e-3
+    check_yaw(np.array([180 - int(row[3])]), yaw_r, corr_r)
+  want = E.error_statistics(m[:, 2], m[:, 3], gt[:, 2], gt[:, 3])
+  assert stats == want and stats['yaw_pairs'] == 4
