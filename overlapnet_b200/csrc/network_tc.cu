@@ -41,6 +41,8 @@ constexpr int PAIR_ROWS = NB * NB;      // 576 rows of c_conv2 output per pair
 constexpr long long kWaitCycles = 1ll << 28;
 constexpr int K4_PITCH = CF + 8;        // fp16 row pitch of L / R for k_delta_conv1_tc: 272 B => conflict-free LDS.128 across rows
 
+constexpr int kLegPartTiles = 320;       // (output tile, split) slots of the leg's split-K workspace
+
 struct TcState {
   __half* w1p = nullptr;        // [60 steps][4][64][8]
   __half* w2p = nullptr;        // [15 di][128 n][64 o] SWIZZLE_128B tiles
@@ -55,6 +57,8 @@ struct TcState {
   int leg_slabs[kMaxLegLayers] = {};
   int leg_nt[kMaxLegLayers] = {};
   __half* actp[2] = {nullptr, nullptr};
+  float* leg_part = nullptr;     // split-K partial tiles of the latency-mode leg: [kLegPartTiles][128 x 64] fp32
+  int* leg_counters = nullptr;   // [kLegPartTiles * 4] arrival counters (always left at zero)
   __half* l16 = nullptr;        // [max_pairs][360][128]
   __half* r16 = nullptr;        // [max_pairs][360][128] (pair mode) / [1][360][128] (query mode)
   __half* o1 = nullptr;         // [rows_pad/128][15 di][128][64]: SWIZZLE_128B A tiles of c_conv2 (o1_chunk_offset)
@@ -1032,6 +1036,9 @@ struct LegArgs {
   int64_t M;                  // output pixels per run
   __half* out_planes; int64_t out_pitch; int out_run_planes;   // EPI 4
   float* out_f32;                                               // EPI 3
+  int n_split;                // split-K: blockIdx.z = nh * n_split + split; each split takes a slab range
+  float* part;                // [tile][split][16 col4][128 rows] float4 partial accumulators (n_split > 1)
+  int* counters;              // [tile][4 lane quarters] arrival counters, left at zero
 };
 
 template <int EPI>
@@ -1041,11 +1048,15 @@ k_leg_resident_tc(LegArgs g, int* __restrict__ err) {
   LRSmem& S = *reinterpret_cast<LRSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t row0 = (int64_t)blockIdx.x * 128;
-  const int y = blockIdx.y, nh = blockIdx.z;
+  const int y = blockIdx.y, nh = blockIdx.z / g.n_split, split = blockIdx.z % g.n_split;
   const int64_t in_base = (int64_t)(y / g.runs_per_img) * g.in_img_planes + (int64_t)(y % g.runs_per_img) * g.in_run_planes;
   const int n_planes = g.kh * 2 * g.c8in;
   const int n_slabs = g.kh * g.kw * 3;
+  // A single scan gives a layer only 8-56 output tiles, each a serial chain of up to 432 MMAs: the K
+  // loop is split over CTAs (slab ranges) and the last CTA to arrive sums the partials in split order.
+  const int sl0 = (int)((int64_t)n_slabs * split / g.n_split), sl1 = (int)((int64_t)n_slabs * (split + 1) / g.n_split);
   const uint32_t b_bytes = (uint32_t)g.c8in * 64 * 16;
+  const int grp = (int)(LR_B_MAX / b_bytes) > 0 ? (int)(LR_B_MAX / b_bytes) : 1;      // slabs per ring stage
 
   if (tid == 0) {
     mbar_init(&S.a_full, 1);
@@ -1059,19 +1070,38 @@ k_leg_resident_tc(LegArgs g, int* __restrict__ err) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = S.tmem_base;
+  // Programmatic dependent launch: the layers of a single-scan leg are ~10 us kernels in a chain, so
+  // the next layer may start its prologue (barriers, TMEM, weight copies) while this one finishes.
+  // Only the activation window (and everything downstream of it) waits for the previous layer.
+  pdl_launch_dependents();
 
   if (warp == 0) {
+    // weights of the first ring stages do not depend on the previous layer
+    uint32_t s = 0, ph = 0;
+    int sl = sl0;
+    for (; sl < sl1 && s < LR_STAGES; sl += grp) {
+      const int cnt = (sl1 - sl < grp) ? sl1 - sl : grp;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&S.full[s], (uint32_t)cnt * b_bytes);
+        bulk_g2s(S.B[s], g.Bp + ((size_t)nh * n_slabs + sl) * (b_bytes / 2), (uint32_t)cnt * b_bytes, &S.full[s]);
+      }
+      ++s;
+    }
+    if (s == LR_STAGES) { s = 0; ph = 1; }
+    pdl_wait();
     // activation window: one copy per plane, issued by the lanes in parallel
     if (lane == 0) mbar_arrive_expect_tx(&S.a_full, (uint32_t)n_planes * LR_WIN * 16);
     __syncwarp();
     for (int pl = lane; pl < n_planes; pl += 32)
       bulk_g2s(S.A + (size_t)pl * LR_WIN * 16, g.A + ((size_t)(in_base + pl) * g.a_pitch + row0) * 8, LR_WIN * 16, &S.a_full);
-    uint32_t s = 0, ph = 0;
-    for (int sl = 0; sl < n_slabs; ++sl) {
+    // weights: consecutive (dh, dw, term) slabs are contiguous in memory, so a ring stage takes as
+    // many of them as fit (a 2 KB slab per copy made s_conv2 a chain of 135 copy round trips)
+    for (; sl < sl1; sl += grp) {
+      const int cnt = (sl1 - sl < grp) ? sl1 - sl : grp;
       TC_WAIT(&S.empty[s], ph ^ 1, 801);
       if (lane == 0) {
-        mbar_arrive_expect_tx(&S.full[s], b_bytes);
-        bulk_g2s(S.B[s], g.Bp + ((size_t)nh * n_slabs + sl) * (b_bytes / 2), b_bytes, &S.full[s]);
+        mbar_arrive_expect_tx(&S.full[s], (uint32_t)cnt * b_bytes);
+        bulk_g2s(S.B[s], g.Bp + ((size_t)nh * n_slabs + sl) * (b_bytes / 2), (uint32_t)cnt * b_bytes, &S.full[s]);
       }
       __syncwarp();
       if (++s == LR_STAGES) { s = 0; ph ^= 1; }
@@ -1085,42 +1115,87 @@ k_leg_resident_tc(LegArgs g, int* __restrict__ err) {
     const uint32_t bd_hi = (uint32_t)(bd0 >> 32), bd_lo = (uint32_t)bd0;
     TC_WAIT(&S.a_full, 0, 802);
     uint32_t sg = 0, ph = 0, first = 1;
-    for (int dh = 0; dh < g.kh; ++dh) {
-      for (int dw = 0; dw < g.kw; ++dw) {
+    int term = sl0 % 3, dw = (sl0 / 3) % g.kw, dh = sl0 / (3 * g.kw);   // slab = (dh, dw, term); x*w ~= xh*wh + xl*wh + xh*wl
 #pragma unroll 1
-        for (int term = 0; term < 3; ++term) {            // x*w ~= xh*wh + xl*wh + xh*wl
-          TC_WAIT(&S.full[sg], ph, 803);
-          fence_after_sync();
-          if (leader) {
-            const uint32_t kind = (term == 1) ? 1u : 0u;
-            const uint32_t a_k = ad_lo + ((((dh * 2 + kind) * g.c8in) * (LR_WIN * 16) + dw * 16) >> 4);
-            const uint32_t b_k = bd_lo + ((sg * LR_B_MAX) >> 4);
-            for (int c16 = 0; c16 < g.c8in / 2; ++c16) {
-              const uint64_t ad = ((uint64_t)ad_hi << 32) | (uint64_t)(a_k + ((c16 * 2 * (LR_WIN * 16)) >> 4));
-              const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_k + ((c16 * 2 * (64 * 16)) >> 4));
-              mma_ss(tmem, ad, bd, idesc, first ? 0u : 1u);
-              first = 0;
-            }
-            commit(&S.empty[sg]);
+    for (int sl = sl0; sl < sl1; sl += grp) {
+      const int cnt = (sl1 - sl < grp) ? sl1 - sl : grp;
+      TC_WAIT(&S.full[sg], ph, 803);
+      fence_after_sync();
+      for (int j = 0; j < cnt; ++j) {
+        if (leader) {
+          const uint32_t kind = (term == 1) ? 1u : 0u;
+          const uint32_t a_k = ad_lo + ((((dh * 2 + kind) * g.c8in) * (LR_WIN * 16) + dw * 16) >> 4);
+          const uint32_t b_k = bd_lo + ((sg * LR_B_MAX + j * b_bytes) >> 4);
+          for (int c16 = 0; c16 < g.c8in / 2; ++c16) {
+            const uint64_t ad = ((uint64_t)ad_hi << 32) | (uint64_t)(a_k + ((c16 * 2 * (LR_WIN * 16)) >> 4));
+            const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_k + ((c16 * 2 * (64 * 16)) >> 4));
+            mma_ss(tmem, ad, bd, idesc, first ? 0u : 1u);
+            first = 0;
           }
-          first = 0;
-          __syncwarp();
-          if (++sg == LR_STAGES) { sg = 0; ph ^= 1; }
         }
+        first = 0;
+        if (++term == 3) { term = 0; if (++dw == g.kw) { dw = 0; ++dh; } }
       }
+      if (leader) commit(&S.empty[sg]);
+      __syncwarp();
+      if (++sg == LR_STAGES) { sg = 0; ph ^= 1; }
     }
     if (leader) commit(&S.d_full);
     __syncwarp();
   } else if (warp >= 4) {
     const int q = warp & 3;
+    pdl_wait();                               // the split-K workspace and the output planes belong to the previous layer until now
     TC_WAIT(&S.d_full, 0, 804);
     fence_after_sync();
     const int64_t r = row0 + q * 32 + lane;
+    const int nz = gridDim.z / g.n_split;
+    const int tile_id = (int)((blockIdx.y * gridDim.x + blockIdx.x) * nz + nh);
+    const float4* parts = reinterpret_cast<const float4*>(g.part) + (size_t)tile_id * g.n_split * 16 * 128 + q * 32 + lane;
+    bool emit = true;
+    if (g.n_split > 1) {
+      float4* mine = reinterpret_cast<float4*>(g.part) + ((size_t)tile_id * g.n_split + split) * 16 * 128 + q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+          mine[((c0 >> 2) + j4) * 128] = make_float4(__uint_as_float(v[j4 * 4 + 0]), __uint_as_float(v[j4 * 4 + 1]),
+                                                     __uint_as_float(v[j4 * 4 + 2]), __uint_as_float(v[j4 * 4 + 3]));
+      }
+      __threadfence();
+      __syncwarp();
+      int prev = 0;
+      if (lane == 0) prev = atomicAdd(g.counters + tile_id * 4 + q, 1);
+      prev = __shfl_sync(0xffffffffu, prev, 0);
+      emit = (prev == g.n_split - 1);            // this warp's rows are complete in every split
+      if (emit) {
+        __threadfence();
+        if (lane == 0) g.counters[tile_id * 4 + q] = 0;
+      }
+    }
+    if (emit) {
 #pragma unroll 1
     for (int c0 = 0; c0 < 64; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
-      tmem_ld_wait();
+      float v[16];
+      if (g.n_split > 1) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        for (int sp = 0; sp < g.n_split; ++sp) {     // fixed order: bit-reproducible
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 t = __ldcg(parts + ((size_t)sp * 16 + (c0 >> 2) + j4) * 128);
+            v[j4 * 4 + 0] += t.x; v[j4 * 4 + 1] += t.y; v[j4 * 4 + 2] += t.z; v[j4 * 4 + 3] += t.w;
+          }
+        }
+      } else {
+        uint32_t u[16];
+        tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + c0, u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(u[j]);
+      }
       if (r < g.M && nh * 64 + c0 < g.n_valid) {
         if (EPI == 4) {
 #pragma unroll
@@ -1129,8 +1204,8 @@ k_leg_resident_tc(LegArgs g, int* __restrict__ err) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int n = c0 + h8 * 8 + 2 * j;
-              const float a = fmaxf(__uint_as_float(v[h8 * 8 + 2 * j]) + S.bias[n], 0.f);
-              const float b = fmaxf(__uint_as_float(v[h8 * 8 + 2 * j + 1]) + S.bias[n + 1], 0.f);
+              const float a = fmaxf(v[h8 * 8 + 2 * j] + S.bias[n], 0.f);
+              const float b = fmaxf(v[h8 * 8 + 2 * j + 1] + S.bias[n + 1], 0.f);
               const __half2 hi = __floats2half2_rn(a, b);
               const float2 hf = __half22float2(hi);
               const __half2 lo = __floats2half2_rn(a - hf.x, b - hf.y);
@@ -1148,14 +1223,15 @@ k_leg_resident_tc(LegArgs g, int* __restrict__ err) {
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             float4 o;
-            o.x = fmaxf(__uint_as_float(v[j4 * 4 + 0]) + S.bias[c0 + j4 * 4 + 0], 0.f);
-            o.y = fmaxf(__uint_as_float(v[j4 * 4 + 1]) + S.bias[c0 + j4 * 4 + 1], 0.f);
-            o.z = fmaxf(__uint_as_float(v[j4 * 4 + 2]) + S.bias[c0 + j4 * 4 + 2], 0.f);
-            o.w = fmaxf(__uint_as_float(v[j4 * 4 + 3]) + S.bias[c0 + j4 * 4 + 3], 0.f);
+            o.x = fmaxf(v[j4 * 4 + 0] + S.bias[c0 + j4 * 4 + 0], 0.f);
+            o.y = fmaxf(v[j4 * 4 + 1] + S.bias[c0 + j4 * 4 + 1], 0.f);
+            o.z = fmaxf(v[j4 * 4 + 2] + S.bias[c0 + j4 * 4 + 2], 0.f);
+            o.w = fmaxf(v[j4 * 4 + 3] + S.bias[c0 + j4 * 4 + 3], 0.f);
             reinterpret_cast<float4*>(dst)[j4] = o;
           }
         }
       }
+    }
     }
   }
 done:
@@ -1573,6 +1649,8 @@ void tc_free(ovn_handle* h) {
   }
   if (t->pb_l16) cudaFree(t->pb_l16);
   if (t->pb_lc) cudaFree(t->pb_lc);
+  if (t->leg_part) cudaFree(t->leg_part);
+  if (t->leg_counters) cudaFree(t->leg_counters);
   if (t->actp[0]) cudaFree(t->actp[0]);
   if (t->actp[1]) cudaFree(t->actp[1]);
   delete t;
@@ -1718,6 +1796,9 @@ int tc_pack_weights(ovn_handle* h) {
     OVN_CUDA(h, cudaMalloc(&t->actp[b], bytes));
     OVN_CUDA(h, cudaMemset(t->actp[b], 0, bytes));
   }
+  OVN_CUDA(h, cudaMalloc(&t->leg_part, (size_t)kLegPartTiles * 128 * 64 * sizeof(float)));
+  OVN_CUDA(h, cudaMalloc(&t->leg_counters, (size_t)kLegPartTiles * 4 * sizeof(int)));
+  OVN_CUDA(h, cudaMemset(t->leg_counters, 0, (size_t)kLegPartTiles * 4 * sizeof(int)));
   const int64_t maxp = h->cfg.max_batch_pairs;
   t->rows_pad = ((maxp * PAIR_ROWS + 1024 + 255) / 256) * 256;   // tile overrun (512) + window shift (50) slack; whole c_conv2 tile pairs
   OVN_CUDA(h, cudaMalloc(&t->l16, (size_t)maxp * WF * K4_PITCH * sizeof(__half)));
@@ -1819,14 +1900,28 @@ int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cuda
     const bool latency = (int64_t)n * L.h_out * 4 <= h->sm_count;
     if (last && (L.cout != 128 || L.h_out != 1)) OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "tensor-core leg: unexpected last layer");
     if (latency) {
-      const dim3 grid((unsigned)((L.w_out + 127) / 128), (unsigned)(n * L.h_out), (unsigned)((L.cout + 63) / 64));
+      dim3 grid((unsigned)((L.w_out + 127) / 128), (unsigned)(n * L.h_out), (unsigned)((L.cout + 63) / 64));
       LegArgs la = {};
       la.A = a.A; la.a_pitch = a.a_pitch; la.runs_per_img = a.runs_per_img; la.in_img_planes = a.in_img_planes;
       la.in_run_planes = a.in_run_planes; la.kh = L.kh; la.kw = L.kw; la.c8in = L.cin / 8; la.Bp = t->wres[l];
       la.bias = h->d_b[l]; la.n_valid = L.cout; la.M = L.w_out; la.out_planes = a.out_planes; la.out_pitch = a.out_pitch;
       la.out_run_planes = a.out_run_planes; la.out_f32 = d_fv;
-      if (last) k_leg_resident_tc<3><<<grid, G_THREADS, sizeof(LRSmem), s>>>(la, t->d_err);
-      else k_leg_resident_tc<4><<<grid, G_THREADS, sizeof(LRSmem), s>>>(la, t->d_err);
+      // split-K so that a layer's CTAs roughly fill the GPU (>= 3 weight slabs per split)
+      const int base_ctas = (int)(grid.x * grid.y * grid.z), n_slabs_l = L.kh * L.kw * 3;
+      int n_split = h->sm_count / base_ctas;
+      if (n_split > n_slabs_l / 3) n_split = n_slabs_l / 3;
+      if (n_split > kLegPartTiles / base_ctas) n_split = kLegPartTiles / base_ctas;
+      if (n_split < 1) n_split = 1;
+      la.n_split = n_split; la.part = t->leg_part; la.counters = t->leg_counters;
+      grid.z *= n_split;
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = grid; lc.blockDim = dim3(G_THREADS); lc.dynamicSmemBytes = sizeof(LRSmem); lc.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = attr; lc.numAttrs = 1;
+      if (last) OVN_CUDA(h, cudaLaunchKernelEx(&lc, k_leg_resident_tc<3>, la, t->d_err));
+      else OVN_CUDA(h, cudaLaunchKernelEx(&lc, k_leg_resident_tc<4>, la, t->d_err));
     } else {
       const dim3 grid(1, (unsigned)(n * L.h_out), 1);
       if (last) k_gemm_stream_tc<3, 128, 4><<<grid, G_THREADS, sizeof(GSmem<128, 4>), s>>>(a, t->d_err);
