@@ -458,9 +458,11 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_i
               }
               tmem_st_x8(lane_addr + sg * K4_STAGE_COLS + t * 16 + hk * 8, o);
             }
+            K4_TR(q == 0 && lane == 0 && u == u_begin + 2 && grp < 3 && hk == 0, 5 + grp, st, 0, clock64());
           }
           K4_TR(q == 0 && lane == 0 && u == u_begin + 2 && grp < 3, 1 + grp, st, 2, clock64());
           tmem_st_wait();
+          K4_TR(q == 0 && lane == 0 && u == u_begin + 2 && grp < 3, 5 + grp, st, 1, clock64());
           fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive_addr(a_full0 + sg * 8);
@@ -1437,10 +1439,10 @@ k_corr_tc(const __half* __restrict__ Lc, const int32_t* __restrict__ l_idx, cons
     // Lane l holds row i0 + l, registers v[cc] the columns j0 + cc of a 32-column chunk; element
     // (l, cc) lies on diagonal d = l - cc.  A first version walked the columns with a rotating
     // accumulator (two dependent shuffles per column: 60 clk x 192 columns per tile, 3x the MMA time).
-    // Now: (1) each lane rotates its registers by its lane index (5-stage barrel shifter of selects),
-    // which puts diagonal d == m (mod 32) into register m; (2) two masked reduce-scatters (31 shuffles
-    // each, all independent within a stage) leave in lane m the sums of diagonals m and m - 32;
-    // (3) one shared-memory add per lane and chunk, the m - 32 part carried into the next chunk.
+    // Now: two masked reduce-scatters over the lanes (31 shuffles each, all independent within a stage)
+    // whose send register depends on the lane bit, which absorbs the per-lane rotation that lines
+    // the diagonals up: lane m ends with the sums of diagonals m and m - 32; then one shared-memory
+    // add per lane and chunk, the m - 32 part carried into the next chunk.
     const int q = warp & 3, half = (warp - 4) >> 2;        // this warp's chunks: half*3 .. half*3 + 2
     float* my = S.corr[warp - 4];
     uint32_t tileit = 0, rz = 0;      // rz: rendezvous count of the 8 epilogue warps (bounded mbarrier, never bar.sync)
@@ -1464,36 +1466,30 @@ k_corr_tc(const __half* __restrict__ Lc, const int32_t* __restrict__ l_idx, cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.d_empty[buf]);
           }
-          // (1) u[m] = v[(lane - m) & 31]: reverse (free renaming), then rotate right by `lane`
-          float u[32];
-#pragma unroll
-          for (int m = 0; m < 32; ++m) u[m] = __uint_as_float(v[(32 - m) & 31]);
-#pragma unroll
-          for (int b = 0; b < 5; ++b) {
-            const bool on = (lane >> b) & 1;
-            float w[32];
-#pragma unroll
-            for (int m = 0; m < 32; ++m) w[m] = on ? u[(m - (1 << b)) & 31] : u[m];
-#pragma unroll
-            for (int m = 0; m < 32; ++m) u[m] = w[m];
-          }
-          // (2) diagonal m (lanes >= m) and diagonal m - 32 (lanes < m), reduce-scattered to lane m
+          // (1) split every column by the sign of its diagonal: register t holds column t, which lies
+          //     on diagonal lane - t (class m = (lane - t) mod 32): x if t <= lane, y (diagonal m - 32) else
           float x[32], y[32];
 #pragma unroll
-          for (int m = 0; m < 32; ++m) {
-            const bool ge = lane >= m;
-            x[m] = ge ? u[m] : 0.f;
-            y[m] = ge ? 0.f : u[m];
+          for (int t2 = 0; t2 < 32; ++t2) {
+            const bool ge = lane >= t2;
+            const float f = __uint_as_float(v[t2]);
+            x[t2] = ge ? f : 0.f;
+            y[t2] = ge ? 0.f : f;
           }
+          // (2) reduce-scatter over the lanes, low bit first.  Before stage b a lane holds the classes
+          //     with (lane - m) % 2^b == 0 in registers t = (lane - m) mod 32; it keeps those with bit b
+          //     of t clear and hands the others to lane ^ 2^b, in whose frame they sit at t +- 2^b: the
+          //     lane-dependent rotation is absorbed into which static register each lane sends.
 #pragma unroll
-          for (int o = 16; o >= 1; o >>= 1) {
+          for (int b = 0; b < 5; ++b) {
+            const int o = 1 << b;
             const bool up = (lane & o) != 0;
 #pragma unroll
-            for (int k = 0; k < o; ++k) {
-              const float sx = up ? x[k] : x[k + o], kx = up ? x[k + o] : x[k];
-              const float sy = up ? y[k] : y[k + o], ky = up ? y[k + o] : y[k];
-              x[k] = kx + __shfl_xor_sync(0xffffffffu, sx, o);
-              y[k] = ky + __shfl_xor_sync(0xffffffffu, sy, o);
+            for (int tp = 0; tp < 32; tp += 2 * o) {
+              const float sx = up ? x[(tp + o) & 31] : x[(tp - o) & 31];
+              const float sy = up ? y[(tp + o) & 31] : y[(tp - o) & 31];
+              x[tp] += __shfl_xor_sync(0xffffffffu, sx, o);
+              y[tp] += __shfl_xor_sync(0xffffffffu, sy, o);
             }
           }
           // (3) bin of (lane 0, column 0 of the chunk), before wrap

@@ -35,7 +35,10 @@ for grp in range(3):
   print('producer group %d: step  begin  slot_ok  st_issued  arrived' % grp)
   for s in range(60):
     if pr[s, 0]:
-      print('  %2d  %6d  %6d  %6d  %6d' % (s, pr[s, 0] - t0, pr[s, 1] - t0, pr[s, 2] - t0, pr[s, 3] - t0))
+      ex = tr[5 + grp]
+      print('  %2d  %6d  %6d  %6d  %6d   | half0 stores issued +%d, all issued +%d, wait::st +%d, arrive +%d' % (
+          s, pr[s, 0] - t0, pr[s, 1] - t0, pr[s, 2] - t0, pr[s, 3] - t0, ex[s, 0] - pr[s, 1], pr[s, 2] - pr[s, 1],
+          ex[s, 1] - pr[s, 2], pr[s, 3] - ex[s, 1]))
 e = tr[4]
 print('epilogue (jb 1 -> rel. to MMA step 0 of jb 2): wait_begin %d  d_full %d  tile (ld issued, released, staged, stored) %s' %
       (e[0, 0] - t0, e[0, 1] - t0, [(int(e[1 + t, 1] - t0), int(e[1 + t, 0] - t0), int(e[1 + t, 3] - t0), int(e[1 + t, 2] - t0)) for t in range(3)]))
