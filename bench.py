@@ -148,7 +148,7 @@ def run_reference(args):
   val = n / dt
   sample = '%d of the 1101 pairs per step (+1 projection, +1 leg), torch-CPU fp32, delta tensor materialised' % n
   print(json.dumps({
-      'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'pairs/s', 'n_gpus': 0, 'steps': steps,
+      'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'pairs/s', 'n_gpus': args.gpus, 'steps': steps,
       'warmup': min(args.warmup, 1), 'ms_per_step': dt * 1e3 * N_CAND / n, 'higher_is_better': True,
       'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': '1 query x 1101 candidates, geo-only 64x900 (BASELINE config 2), bounded sample'},
