@@ -156,3 +156,25 @@ def test_full_size_1xN_properties():
   assert np.abs(ov.cpu().numpy()[sel] - ov_ref).max() <= OVERLAP_TOL
   check_yaw(yaw.cpu().numpy()[sel], yaw_ref, corr_ref)
   eng.close()
+
+
+def test_single_scan_leg_is_bit_reproducible_and_matches_batched():
+  """The latency-mode leg splits K over CTAs and lets the last CTA to arrive sum the partial tiles in
+  split order (no floating-point atomics): repeated runs are bit-identical, and the result agrees
+  with the batched (streamed-GEMM) path within the leg tolerance."""
+  w = N.glorot_weights(4, MODEL, seed=4)
+  x = synth.range_like_images(21, 6, 4)
+  eng1 = Engine(model=MODEL, precision='f16_tc', max_batch_scans=1, max_batch_pairs=1)     # one scan per launch
+  eng6 = Engine(model=MODEL, precision='f16_tc', max_batch_scans=6, max_batch_pairs=1)     # all six in one launch
+  eng1.load_weights(w); eng6.load_weights(w)
+  xt = torch.from_numpy(x).to(eng1.device)
+  a = eng1.leg(xt)
+  for _ in range(3):
+    assert torch.equal(eng1.leg(xt), a)
+  b = eng6.leg(xt)
+  ref = N.leg_forward(x, w, MODEL)[:, 0]
+  scale = np.abs(ref).max()
+  assert np.abs(a.cpu().numpy() - ref).max() / scale <= 4e-3
+  assert np.abs(b.cpu().numpy() - ref).max() / scale <= 4e-3
+  assert (a - b).abs().max().item() / scale <= 1e-4
+  eng1.close(); eng6.close()
