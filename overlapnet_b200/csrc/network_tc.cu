@@ -115,7 +115,6 @@ constexpr int K4_STAGE_COLS = 48;
 constexpr int K4_STEPS = 60;            // 4 channel chunks x 15 dj per jb
 constexpr int K4_BSLICE = 4096;         // bytes of W1 per step: [4 k8][64 o][8]
 constexpr int K4_RWIN_BYTES = S15 * K4_PITCH * 2;   // the 15 RIGHT rows one jb touches
-constexpr int K4_PHASE_CLK = 2200;      // start stagger of the MMA issuer: 8 phases x 2200 clk ~ one unit (60 steps x ~290 clk)
 
 // o1 layout ("SWIZZLE_128B tiles"): the A operand of c_conv2, stored as the shared-memory image its
 // MMAs read, so that c_conv2 loads a [128 rows x 64 K] tile with ONE 16 KB bulk copy:
@@ -241,13 +240,6 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_i
       const uint32_t a_full0 = smem_u32(&S.a_full[0]), b_full0 = smem_u32(&S.b_full[0]);
       uint32_t ui = 0, bg = 0, bph = 0;
       bool ready = false, bready = false;
-      {
-        // All CTAs run the same schedule, so without a phase offset their epilogues store 46 KB each
-        // at the same instant (a 6.8 MB burst every unit, measured at ~16 B/clk/SM: the issuer then
-        // waits ~4000 clk for its accumulators).  Eight start phases spread the bursts over the unit.
-        const long long t_go = clock64() + (long long)(blockIdx.x & 7) * K4_PHASE_CLK;
-        while (clock64() < t_go) { }
-      }
       for (int u = u_begin; u < u_end; ++u, ++ui) {
 #pragma unroll 1
         for (uint32_t o = 0; o < K4_STEPS / K4_STAGES; ++o) {
