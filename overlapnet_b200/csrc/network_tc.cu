@@ -50,7 +50,6 @@ struct TcState {
   float* b2eff = nullptr;       // c_conv2 bias + the c_conv1 bias pushed through W2 (both layers are linear)
   // tensor-core leg (layers 2..): packed weights + copy tables per layer, ping-pong activation planes
   __half* wleg[kMaxLegLayers] = {};      // [1][n_slabs][4][NT][8]   (throughput mode)
-  __half* wleg64[kMaxLegLayers] = {};    // [cout/64][n_slabs][4][64][8] (streamed, 64-wide)
   __half* wres[kMaxLegLayers] = {};      // [cout/64][kh*kw*3][C_in/8][64][8] (latency mode, resident activations)
   int* leg_plane[kMaxLegLayers] = {};
   int* leg_shift[kMaxLegLayers] = {};
@@ -475,13 +474,15 @@ done:
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_gemm_stream_tc
+// k_gemm_stream_tc -- the batched leg (many scans per launch): one CTA per output image row,
+// D[512 rows x NT] += sum over K slabs of A_slab[512 x 32] * B_slab[NT x 32]^T with both operands
+// streamed global -> shared by cp.async.bulk in the C8-interleaved layout; a per-copy row shift is
+// the convolution tap along the row (implicit im2col at the copy level).  The single-scan leg uses
+// k_leg_resident_tc instead (activation window resident, split-K, programmatic dependent launch).
 // ------------------------------------------------------------------------------------------------
 constexpr int G_THREADS = 256;
 
-// TILES = 128-row tiles per CTA: 4 for throughput (W slabs are reused by four tiles, 4-deep ring
-// of 40 KB stages), 1 for latency (single-scan leg: 4x more CTAs, 12-deep ring of 12-16 KB stages
-// so that the L2 round trip of a slab is hidden by ring depth rather than by work per stage).
+// TILES = 128-row tiles per CTA: 4 (W slabs are reused by four tiles, 4-deep ring of 40 KB stages)
 template <int NT, int TILES>
 struct GCfg {
   static constexpr int ROWS = TILES * 128;
@@ -518,10 +519,8 @@ struct GemmArgs {
   int runs_per_img;           // blockIdx.y = img * runs_per_img + run
   int in_img_planes;          // planes per input image
   int in_run_planes;          // plane advance per run (stride_h * C8_in)
-  // epilogue 1: bias + ReLU -> fp16 planes [y * out_run_planes + n/8][row][8]
+  // epilogue 4: bias + ReLU -> hi/lo fp16 planes [y * out_run_planes + {hi, lo}][n/8][row][8]
   __half* out_planes; int64_t out_pitch; int out_run_planes;
-  // epilogue 2: bias + ReLU -> dot with the Dense kernel -> per-row partial sums
-  const float* wd; float* partial; int grid_w, valid_w, valid_h, n_total;
   // epilogue 3: bias + ReLU -> fp32 row-major [y][row][NT]
   float* out_f32;
   int n_valid;                // output channels actually present (<= NT); 0 = NT
@@ -608,7 +607,7 @@ k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
 #pragma unroll 1
     for (int t = 0; t < TILES; ++t) {
       const int64_t r = row0 + t * 128 + q * 32 + lane;
-      if (EPI == 1 || EPI == 3 || EPI == 4) {
+      {
 #pragma unroll 1
         for (int c0 = 0; c0 < NT; c0 += 16) {
           uint32_t v[16];
@@ -639,21 +638,6 @@ k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
                 *reinterpret_cast<uint4*>(g.out_planes + ((size_t)(plane + g.out_run_planes / 2) * g.out_pitch + r) * 8) =
                     make_uint4(pl[0], pl[1], pl[2], pl[3]);
               }
-            } else if (EPI == 1) {
-#pragma unroll
-              for (int h8 = 0; h8 < 2; ++h8) {
-                uint32_t pk[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int n = c0 + h8 * 8 + 2 * j;
-                  __half2 hh = __floats2half2_rn(fmaxf(__uint_as_float(v[h8 * 8 + 2 * j]) + S.bias[n], 0.f),
-                                                 fmaxf(__uint_as_float(v[h8 * 8 + 2 * j + 1]) + S.bias[n + 1], 0.f));
-                  pk[j] = *reinterpret_cast<uint32_t*>(&hh);
-                }
-                const int64_t plane = (int64_t)y * g.out_run_planes + nh * (NT / 8) + (c0 >> 3) + h8;
-                *reinterpret_cast<uint4*>(g.out_planes + ((size_t)plane * g.out_pitch + r) * 8) =
-                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              }
             } else {
               float* dst = g.out_f32 + ((size_t)y * g.M + r) * (g.n_valid ? g.n_valid : NT) + nh * NT + c0;
 #pragma unroll
@@ -668,31 +652,6 @@ k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
             }
           }
         }
-      } else {
-        // row r = pair * (grid_w*grid_w) + y * grid_w + x ; valid output pixel iff y < valid_h, x < valid_w
-        const int per = g.grid_w * g.grid_w;
-        const int rem = (int)(r % per);
-        const int yy = rem / g.grid_w, xx = rem - yy * g.grid_w;
-        const bool valid = (r < g.M) && (yy < g.valid_h) && (xx < g.valid_w);
-        const float* wrow = g.wd + ((size_t)(valid ? (yy * g.valid_w + xx) : 0) * g.n_total + nh * NT);
-        float acc = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < NT; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * NT + c0, v);
-          tmem_ld_wait();
-          if (valid) {
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + c0) + j4);
-              acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 0]) + S.bias[c0 + j4 * 4 + 0], 0.f), w.x, acc);
-              acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 1]) + S.bias[c0 + j4 * 4 + 1], 0.f), w.y, acc);
-              acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 2]) + S.bias[c0 + j4 * 4 + 2], 0.f), w.z, acc);
-              acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 3]) + S.bias[c0 + j4 * 4 + 3], 0.f), w.w, acc);
-            }
-          }
-        }
-        if (r < g.M) g.partial[r * 2 + nh] = valid ? acc : 0.f;
       }
     }
   }
@@ -1630,7 +1589,6 @@ void tc_free(ovn_handle* h) {
   for (void* b : bufs) if (b) cudaFree(b);
   for (int l = 0; l < kMaxLegLayers; ++l) {
     if (t->wleg[l]) cudaFree(t->wleg[l]);
-    if (t->wleg64[l]) cudaFree(t->wleg64[l]);
     if (t->wres[l]) cudaFree(t->wres[l]);
     if (t->leg_plane[l]) cudaFree(t->leg_plane[l]);
     if (t->leg_shift[l]) cudaFree(t->leg_shift[l]);
@@ -1743,19 +1701,11 @@ int tc_pack_weights(ovn_handle* h) {
           }
       }
     }
-    // the same weights sliced into 64-channel halves for the latency variant
     const int nz = (L.cout + 63) / 64;
-    std::vector<__half> bp64((size_t)nz * n_slabs * 4 * 64 * 8, __float2half(0.f));
-    for (int z = 0; z < nz; ++z)
-      for (int e = 0; e < n_slabs * 4; ++e)
-        for (int n = 0; n < 64 && z * 64 + n < nt; ++n)
-          for (int k = 0; k < 8; ++k)
-            bp64[(((size_t)z * n_slabs * 4 + e) * 64 + n) * 8 + k] = bp[((size_t)e * nt + z * 64 + n) * 8 + k];
     t->leg_slabs[l] = n_slabs;
     t->leg_nt[l] = nt;
     int rc2;
     if ((rc2 = upload_vec(h, &t->wleg[l], bp)) != OVN_OK) return rc2;
-    if ((rc2 = upload_vec(h, &t->wleg64[l], bp64)) != OVN_OK) return rc2;
     {
       // resident-activation layout: slab = (dh, dw, term), rows = all C_in/8 chunks, 64 output channels
       const int nsl = L.kh * L.kw * 3;
@@ -1809,10 +1759,8 @@ int tc_pack_weights(ovn_handle* h) {
 #define OVN_GEMM_ATTR(E, N, T)                                                                                  \
   OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<E, N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                    (int)sizeof(GSmem<N, T>)))
-  OVN_GEMM_ATTR(1, 128, 4); OVN_GEMM_ATTR(2, 128, 4);
   OVN_CUDA(h, cudaFuncSetAttribute(k_conv3_resident_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(C3Smem)));
   OVN_GEMM_ATTR(4, 64, 4); OVN_GEMM_ATTR(4, 128, 4); OVN_GEMM_ATTR(3, 128, 4);
-  OVN_GEMM_ATTR(4, 64, 1); OVN_GEMM_ATTR(3, 64, 1);
   OVN_CUDA(h, cudaFuncSetAttribute(k_leg_layer1_direct<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   OVN_CUDA(h, cudaFuncSetAttribute(k_leg_layer1_direct<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   OVN_CUDA(h, cudaFuncSetAttribute(k_leg_resident_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LRSmem)));
