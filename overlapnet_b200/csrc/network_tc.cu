@@ -1842,10 +1842,13 @@ int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cuda
       la.in_run_planes = a.in_run_planes; la.kh = L.kh; la.kw = L.kw; la.c8in = L.cin / 8; la.Bp = t->wres[l];
       la.bias = h->d_b[l]; la.n_valid = L.cout; la.M = L.w_out; la.out_planes = a.out_planes; la.out_pitch = a.out_pitch;
       la.out_run_planes = a.out_run_planes; la.out_f32 = d_fv;
-      // split-K so that a layer's CTAs roughly fill the GPU (>= 3 weight slabs per split)
+      // split-K so that a layer's CTAs roughly fill the GPU
       const int base_ctas = (int)(grid.x * grid.y * grid.z), n_slabs_l = L.kh * L.kw * 3;
+      // measured (single scan, whole leg): >= 1 / 2 / 3 / 4 / 6 / 9 / 18 slabs per split ->
+      // 0.196 / 0.165 / 0.151 / 0.144 / 0.138 / 0.152 / 0.154 ms; filling the GPU twice over is worse
+      constexpr int kMinSlabsPerSplit = 6;
       int n_split = h->sm_count / base_ctas;
-      if (n_split > n_slabs_l / 3) n_split = n_slabs_l / 3;
+      if (n_split > n_slabs_l / kMinSlabsPerSplit) n_split = n_slabs_l / kMinSlabsPerSplit;
       if (n_split > kLegPartTiles / base_ctas) n_split = kLegPartTiles / base_ctas;
       if (n_split < 1) n_split = 1;
       la.n_split = n_split; la.part = t->leg_part; la.counters = t->leg_counters;

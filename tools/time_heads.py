@@ -1,4 +1,5 @@
-"""Per-kernel CUDA-event times of the 1 x 1101 heads (development aid for parameter sweeps)."""
+"""Per-kernel CUDA-event times of the 1 x 1101 heads and of a single-scan leg (development aid for
+parameter sweeps: OVN_* environment switches are read once per process)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -18,7 +19,12 @@ eng.profile_enable(True)
 for _ in range(10): eng.heads_1vsN(bank, bank[0], n_cand=n)
 torch.cuda.synchronize()
 out = []
-for k in ('delta_conv1', 'conv2', 'conv3', 'corr'):
+x = torch.rand((1, 64, 900, 4), device='cuda', generator=g) * 30
+for _ in range(3): eng.leg(x)
+torch.cuda.synchronize()
+for _ in range(20): eng.leg(x)
+torch.cuda.synchronize()
+for k in ('delta_conv1', 'conv2', 'conv3', 'corr', 'leg'):
   ms, c = eng.profile_read(k)
   out.append('%s %.4f' % (k, ms / max(c, 1)))
 print(os.environ.get('TAG', ''), ' '.join(out))
