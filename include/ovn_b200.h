@@ -184,6 +184,28 @@ int ovn_bank_prepare(ovn_handle* h, const float* d_bank, int64_t bank_capacity, 
                      void* stream);
 int ovn_bank_release(ovn_handle* h, const float* d_bank);
 
+/* ---- deferred device errors ------------------------------------------------------------------
+ * The device-pointer entry points never synchronise, so two classes of error can only be detected on
+ * the device: an index outside [0, bank_size) (or, for a resident bank, a row that was never
+ * prepared), and a bounded pipeline-barrier wait of a tensor-core kernel that timed out (GPU
+ * time-slicing, debuggers).  Both raise a flag on the device; the kernels that write overlap / yaw
+ * then POISON their outputs (overlap = NaN, yaw = INT32_MIN) so garbage never looks valid, indices are
+ * clamped so no out-of-bounds read happens, and the flag is turned into a status by the next entry point
+ * that synchronises anyway: ovn_check (synchronises `stream`), the *_host entry points and
+ * ovn_profile_read.  OVN_ERR_INVALID_ARG for index errors, OVN_ERR_CUDA for time-outs; the flag is
+ * cleared when it is reported. */
+int ovn_check(ovn_handle* h, void* stream);
+
+/* ---- feature centre of the tensor-core delta head ------------------------------------------------
+ * DeltaLayer only sees |l - r| (generateNet.py:59), which is invariant to a common per-channel offset:
+ * the fp16 operand copies of the volumes are stored as fp16(x - mu[c]), which shrinks their rounding
+ * error (measured: 3x on leg outputs, profiles/r2_precision_budget.txt).  mu is calibrated automatically
+ * on the first volumes the handle sees (first ovn_bank_prepare rows, else the first RIGHT volume) and
+ * then frozen until ovn_finalize_weights; ovn_set_feature_center(h, mu[128]) fixes it explicitly
+ * (NULL = back to automatic; not allowed while a bank is resident).  No effect for precision fp32. */
+int ovn_set_feature_center(ovn_handle* h, const float* h_mu);
+int ovn_get_feature_center(ovn_handle* h, float* h_mu /* [128] */, int32_t* is_set);
+
 /* ---- host-buffer convenience entry points (what a non-CUDA caller binds; bench.py e2e) ------ */
 /* Raw clouds on the host -> feature volumes on the host. */
 int ovn_encode_clouds_host(ovn_handle* h, const float* h_points, const int64_t* h_offsets,

@@ -3,6 +3,7 @@ with the repo snapshot to the GPU box; nothing is JIT-compiled at import time.""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
@@ -27,11 +28,23 @@ def build(force=False, verbose=False):
   deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
   deps.append(os.path.join(HERE, '..', 'include', 'ovn_b200.h'))
   if force or _newer(LIB, deps):
-    cmd = [nvcc] + NVCC_FLAGS + ['-shared', '-o', LIB] + srcs
-    if verbose:
-      cmd.insert(1, '-Xptxas=-v')
-      print(' '.join(cmd), file=sys.stderr)
-    subprocess.check_call(cmd)
+    # one object per translation unit, compiled in parallel, then linked
+    objdir = os.path.join(HERE, 'build')
+    os.makedirs(objdir, exist_ok=True)
+    hdrs = [d for d in deps if d not in srcs]
+
+    def compile_one(src):
+      obj = os.path.join(objdir, os.path.basename(src)[:-3] + '.o')
+      if force or _newer(obj, [src] + hdrs):
+        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas=-v'] if verbose else []) + ['-c', '-o', obj, src]
+        if verbose:
+          print(' '.join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
+      return obj
+
+    with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+      objs = list(ex.map(compile_one, srcs))
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ['-shared', '-o', LIB] + objs)
   probe_src = os.path.join(CSRC, 'umma_probe.cu')
   if os.path.exists(probe_src) and (force or _newer(PROBE, [probe_src] + deps)):
     subprocess.check_call([nvcc] + NVCC_FLAGS + ['-o', PROBE, probe_src])

@@ -25,6 +25,45 @@ static __global__ void k_iota(int32_t* p, int n, int start) {
   if (i < n) p[i] = start + i;
 }
 
+static __global__ void k_sanitize_idx(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n, int64_t limit,
+                                      int code, int* __restrict__ err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t v = in[i];
+  if (v < 0 || v >= limit) {
+    atomicCAS(err, 0, code);              // the first error wins; results of this call are poisoned by the finalize kernels
+    v = v < 0 ? 0 : limit - 1;
+  }
+  out[i] = (int32_t)v;
+}
+
+namespace ovn {
+
+int sanitize_indices(ovn_handle* h, const int32_t* d_in, int n, int64_t limit, int code, int32_t* d_out, cudaStream_t s) {
+  if (n <= 0) return OVN_OK;
+  k_sanitize_idx<<<(n + 255) / 256, 256, 0, s>>>(d_in, d_out, n, limit < 1 ? 1 : limit, code, h->d_err);
+  OVN_LAUNCH_CHECK(h);
+  return OVN_OK;
+}
+
+// The caller has queued everything on `s`; this copies the flag back, synchronises `s` and maps a
+// non-zero flag to a status (the flag is cleared so that the handle stays usable).
+int check_device_error(ovn_handle* h, cudaStream_t s) {
+  int* hp = reinterpret_cast<int*>(h->h_pinned);
+  if (!hp || !h->d_err) return OVN_OK;
+  OVN_CUDA(h, cudaMemcpyAsync(hp, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  OVN_CUDA(h, cudaStreamSynchronize(s));
+  const int e = *hp;
+  if (e == 0) return OVN_OK;
+  OVN_CUDA(h, cudaMemsetAsync(h->d_err, 0, sizeof(int), s));
+  if (e == kErrBadIndex) OVN_SET_ERR(h, OVN_ERR_INVALID_ARG, "a pair / candidate index is outside [0, bank_size)");
+  if (e == kErrRowNotPrepared)
+    OVN_SET_ERR(h, OVN_ERR_INVALID_ARG, "resident bank: an indexed row was never passed to ovn_bank_prepare");
+  OVN_SET_ERR(h, OVN_ERR_CUDA, "tensor-core pipeline barrier timed out (code %d); outputs of the call are poisoned (NaN / INT32_MIN)", e);
+}
+
+}  // namespace ovn
+
 extern "C" {
 
 int ovn_abi_version(void) { return OVN_ABI_VERSION; }
@@ -171,6 +210,13 @@ int ovn_create(const ovn_config* cfg, ovn_handle** out) {
   CREATE_CUDA(cudaMalloc(&h->d_act[1], h->cap_act * sizeof(float)));
   CREATE_CUDA(cudaMalloc(&h->d_query_fv, (size_t)Wf * kFeatC * sizeof(float)));
   CREATE_CUDA(cudaMalloc(&h->d_idx_tmp, (size_t)2 * c.max_batch_pairs * sizeof(int32_t)));
+  CREATE_CUDA(cudaMalloc(&h->d_idx_san, (size_t)3 * c.max_batch_pairs * sizeof(int32_t)));   // left, right, resident-row check
+  CREATE_CUDA(cudaMalloc(&h->d_err, sizeof(int)));
+  CREATE_CUDA(cudaMemset(h->d_err, 0, sizeof(int)));
+  CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_bank, cudaEventDisableTiming));
+  // pinned staging of the host entry points: [err int, pad][offsets 2 x i64][cand idx][overlap][yaw]
+  h->cap_pinned = 64 + (int64_t)c.max_batch_pairs * 12;
+  CREATE_CUDA(cudaHostAlloc(&h->h_pinned, (size_t)h->cap_pinned, cudaHostAllocDefault));
   CREATE_CUDA(cudaMalloc(&h->d_logit, (size_t)c.max_batch_pairs * sizeof(float)));
   if (h->net_ok) CREATE_CUDA(cudaMalloc(&h->d_G, (size_t)c.max_batch_pairs * Wf * Wf * sizeof(float)));
   if (c.precision == OVN_PREC_FP32 && h->net_ok) {
@@ -186,15 +232,17 @@ int ovn_create(const ovn_config* cfg, ovn_handle** out) {
 
 int ovn_destroy(ovn_handle* h) {
   if (!h) return OVN_OK;
+  DeviceGuard guard(h);
   tc_free(h);
   for (auto& p : h->d_w) if (p) cudaFree(p);
   for (auto& p : h->d_b) if (p) cudaFree(p);
   for (auto& p : h->d_w16) if (p) cudaFree(p);
   void* bufs[] = {h->d_keys, h->d_valid_words, h->d_word_prefix, h->d_scan_tmp, h->d_act[0], h->d_act[1],
                   h->d_input, h->d_o1, h->d_o2, h->d_logit, h->d_G, h->d_idx_tmp, h->d_query_fv,
-                  h->d_stage_points, h->d_stage_offsets};
+                  h->d_stage_points, h->d_stage_offsets, h->d_idx_san, h->d_err};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->ev_bank) cudaEventDestroy(h->ev_bank);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   for (auto& v : h->prof_ev) for (cudaEvent_t e : v) cudaEventDestroy(e);
   delete h;
@@ -203,12 +251,14 @@ int ovn_destroy(ovn_handle* h) {
 
 int ovn_profile_enable(ovn_handle* h, int on) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   h->profiling = on != 0;
   return OVN_OK;
 }
 
 int ovn_profile_read(ovn_handle* h, const char* kernel, double* total_ms, int64_t* launches) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   if (!kernel || !total_ms || !launches) OVN_SET_ERR(h, OVN_ERR_INVALID_ARG, "ovn_profile_read: NULL argument");
   static const char* names[kProfKinds] = {"delta_conv1", "conv2", "conv3", "corr", "project_scatter",
                                           "project_gather", "leg"};
@@ -216,6 +266,7 @@ int ovn_profile_read(ovn_handle* h, const char* kernel, double* total_ms, int64_
   for (int i = 0; i < kProfKinds; ++i) if (strcmp(kernel, names[i]) == 0) kind = i;
   if (kind < 0) OVN_SET_ERR(h, OVN_ERR_INVALID_ARG, "ovn_profile_read: unknown kernel '%s'", kernel);
   OVN_CUDA(h, cudaDeviceSynchronize());
+  { int rc = check_device_error(h, h->own_stream); if (rc != OVN_OK) return rc; }
   std::vector<cudaEvent_t>& ev = h->prof_ev[kind];
   double ms = 0;
   int64_t n = 0;
@@ -242,6 +293,7 @@ static const ConvSpec* find_layer(const ovn_handle* h, const char* name, int* sl
 int ovn_set_weights(ovn_handle* h, const char* name, const float* k, const int64_t* dims, int32_t ndim,
                     const float* bias, int64_t bias_len) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   if (!name || !k || !dims || !bias) OVN_SET_ERR(h, OVN_ERR_INVALID_ARG, "ovn_set_weights: NULL argument");
   if (!h->net_ok) OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "ovn_set_weights: %s", h->net_error.c_str());
   int slot = -1;
@@ -287,6 +339,7 @@ static int upload(ovn_handle* h, int slot, const LayerWeights& w) {
 
 int ovn_finalize_weights(ovn_handle* h) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   if (!h->net_ok) OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "ovn_finalize_weights: %s", h->net_error.c_str());
   for (int l = 0; l < h->n_leg; ++l) {
     auto it = h->host_w.find(h->leg[l].name);
@@ -319,6 +372,7 @@ int ovn_project_batch(ovn_handle* h, const float* d_points, const int64_t* d_off
                       int64_t n_total, float max_range, float* d_range, float* d_vertex, float* d_intensity,
                       int32_t* d_idx, void* stream) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   REQUIRE(h, n_scans >= 0 && n_total >= 0, "negative size");
   REQUIRE(h, n_scans == 0 || d_offsets, "d_offsets is NULL");
   REQUIRE(h, n_total == 0 || d_points, "d_points is NULL");
@@ -329,6 +383,7 @@ int ovn_project_batch(ovn_handle* h, const float* d_points, const int64_t* d_off
 int ovn_normals_batch(ovn_handle* h, const float* d_range, const float* d_vertex, int32_t n_scans, float* d_normal,
                       void* stream) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   REQUIRE(h, n_scans >= 0, "negative size");
   REQUIRE(h, n_scans == 0 || (d_range && d_vertex && d_normal), "NULL image pointer");
   return normals_batch(h, d_range, d_vertex, n_scans, d_normal, (cudaStream_t)stream);
@@ -337,6 +392,7 @@ int ovn_normals_batch(ovn_handle* h, const float* d_range, const float* d_vertex
 int ovn_semantic_batch(ovn_handle* h, const int32_t* d_idx, const float* d_probs, const int64_t* d_offsets,
                        int32_t n_scans, int32_t n_classes, float* d_out, void* stream) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   REQUIRE(h, n_scans >= 0 && n_classes > 0, "bad size");
   REQUIRE(h, n_scans == 0 || (d_idx && d_probs && d_offsets && d_out), "NULL pointer");
   return semantic_batch(h, d_idx, d_probs, d_offsets, n_scans, n_classes, d_out, (cudaStream_t)stream);
@@ -346,6 +402,7 @@ int ovn_gt_range_batch(ovn_handle* h, const float* d_points, const int64_t* d_of
                        int64_t n_total, const double* d_pose_ref, const double* d_pose_cur_inv, float max_range,
                        float* d_range, void* stream) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   REQUIRE(h, n_scans >= 0 && n_total >= 0, "negative size");
   REQUIRE(h, n_scans == 0 || (d_offsets && d_range && (d_points || n_total == 0)), "NULL pointer");
   return gt_range_batch(h, d_points, d_offsets, n_scans, n_total, d_pose_ref, d_pose_cur_inv, max_range, d_range,
@@ -355,6 +412,7 @@ int ovn_gt_range_batch(ovn_handle* h, const float* d_points, const int64_t* d_of
 int ovn_gt_overlap_count(ovn_handle* h, const float* d_ref_ranges, const float* d_cur_range, int32_t n_scans,
                          int32_t* d_counts, void* stream) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   REQUIRE(h, n_scans >= 0, "negative size");
   REQUIRE(h, d_cur_range && d_counts && (n_scans == 0 || d_ref_ranges), "NULL pointer");
   return gt_overlap_count(h, d_ref_ranges, d_cur_range, n_scans, d_counts, (cudaStream_t)stream);
@@ -363,6 +421,7 @@ int ovn_gt_overlap_count(ovn_handle* h, const float* d_ref_ranges, const float* 
 int ovn_preprocess_batch(ovn_handle* h, const float* d_points, const int64_t* d_offsets, int32_t n_scans,
                          int64_t n_total, const float* d_probs, float* d_input, void* stream) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   REQUIRE(h, n_scans >= 0 && n_total >= 0, "negative size");
   REQUIRE(h, n_scans == 0 || (d_offsets && d_input), "NULL pointer");
   return preprocess_batch(h, d_points, d_offsets, n_scans, n_total, d_probs, d_input, (cudaStream_t)stream);
@@ -371,6 +430,7 @@ int ovn_preprocess_batch(ovn_handle* h, const float* d_points, const int64_t* d_
 int ovn_pack_input(ovn_handle* h, const float* d_depth, const float* d_normal, const float* d_prob,
                    const float* d_intensity, int32_t n_scans, float* d_input, void* stream) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   REQUIRE(h, n_scans >= 0, "negative size");
   REQUIRE(h, (d_depth != nullptr) == (h->cfg.use_depth != 0), "depth pointer does not match use_depth");
   REQUIRE(h, (d_normal != nullptr) == (h->cfg.use_normals != 0), "normal pointer does not match use_normals");
@@ -381,6 +441,7 @@ int ovn_pack_input(ovn_handle* h, const float* d_depth, const float* d_normal, c
 
 int ovn_leg_forward(ovn_handle* h, const float* d_input, int32_t n_scans, float* d_fv, void* stream) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   REQUIRE(h, n_scans >= 0, "negative size");
   if (n_scans == 0) return OVN_OK;
   REQUIRE(h, d_input && d_fv, "NULL pointer");
@@ -398,42 +459,64 @@ int ovn_leg_forward(ovn_handle* h, const float* d_input, int32_t n_scans, float*
   return OVN_OK;
 }
 
-static int heads_dispatch(ovn_handle* h, const float* d_bank, const float* d_query, const int32_t* d_left,
-                          const int32_t* d_right, int n, float* d_overlap, int32_t* d_yaw, float* d_corr,
-                          cudaStream_t s) {
+static int heads_dispatch(ovn_handle* h, const float* d_bank, int64_t bank_size, const float* d_query,
+                          const int32_t* d_left, const int32_t* d_right, int n, float* d_overlap, int32_t* d_yaw,
+                          float* d_corr, cudaStream_t s) {
   if (!h->net_ok) OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "heads: %s", h->net_error.c_str());
   if (!h->weights_ready) OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "heads: weights not finalised");
-  return (h->cfg.precision == OVN_PREC_F16_TC)
-             ? heads_forward_tc(h, d_bank, d_query, d_left, d_right, n, d_overlap, d_yaw, d_corr, s)
-             : heads_forward_fp32(h, d_bank, d_query, d_left, d_right, n, d_overlap, d_yaw, d_corr, s);
+  if (bank_size <= 0) OVN_SET_ERR(h, OVN_ERR_INVALID_ARG, "heads: bank_size must be positive");
+  // Every index list is bounds-checked on the device (no host sync): out-of-range entries are clamped,
+  // the error flag is raised, the finalize kernels poison the outputs and the next synchronising
+  // entry point (ovn_check, *_host, ovn_profile_read) returns OVN_ERR_INVALID_ARG.
+  const int maxp = h->cfg.max_batch_pairs;
+  const int Wf = h->cfg.leg_output_width;
+  for (int p0 = 0; p0 < n; p0 += maxp) {
+    const int np = (n - p0 < maxp) ? n - p0 : maxp;
+    int32_t* l = h->d_idx_san;
+    int32_t* r = d_right ? h->d_idx_san + maxp : nullptr;
+    int rc = sanitize_indices(h, d_left + p0, np, bank_size, kErrBadIndex, l, s);
+    if (rc == OVN_OK && d_right) rc = sanitize_indices(h, d_right + p0, np, bank_size, kErrBadIndex, r, s);
+    if (rc != OVN_OK) return rc;
+    float* corr = d_corr ? d_corr + (size_t)p0 * Wf : nullptr;
+    rc = (h->cfg.precision == OVN_PREC_F16_TC)
+             ? heads_forward_tc(h, d_bank, d_query, l, r, np, d_overlap + p0, d_yaw + p0, corr, s)
+             : heads_forward_fp32(h, d_bank, d_query, l, r, np, d_overlap + p0, d_yaw + p0, corr, s);
+    if (rc != OVN_OK) return rc;
+  }
+  return OVN_OK;
 }
 
 int ovn_heads_forward(ovn_handle* h, const float* d_bank, int64_t bank_size, const int32_t* d_left,
                       const int32_t* d_right, int32_t n_pairs, float* d_overlap, int32_t* d_yaw, float* d_corr,
                       void* stream) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   REQUIRE(h, n_pairs >= 0 && bank_size >= 0, "negative size");
   if (n_pairs == 0) return OVN_OK;
   REQUIRE(h, d_bank && d_left && d_right && d_overlap && d_yaw, "NULL pointer");
-  return heads_dispatch(h, d_bank, nullptr, d_left, d_right, n_pairs, d_overlap, d_yaw, d_corr, (cudaStream_t)stream);
+  return heads_dispatch(h, d_bank, bank_size, nullptr, d_left, d_right, n_pairs, d_overlap, d_yaw, d_corr,
+                        (cudaStream_t)stream);
 }
 
 int ovn_heads_1vsN(ovn_handle* h, const float* d_bank, int64_t bank_size, const float* d_query,
                    const int32_t* d_cand_idx, int32_t n_cand, float* d_overlap, int32_t* d_yaw, float* d_corr,
                    void* stream) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   REQUIRE(h, n_cand >= 0 && bank_size >= 0, "negative size");
   if (n_cand == 0) return OVN_OK;
   REQUIRE(h, d_bank && d_query && d_overlap && d_yaw, "NULL pointer");
   cudaStream_t s = (cudaStream_t)stream;
-  if (d_cand_idx) return heads_dispatch(h, d_bank, d_query, d_cand_idx, nullptr, n_cand, d_overlap, d_yaw, d_corr, s);
+  if (d_cand_idx)
+    return heads_dispatch(h, d_bank, bank_size, d_query, d_cand_idx, nullptr, n_cand, d_overlap, d_yaw, d_corr, s);
+  REQUIRE(h, n_cand <= bank_size, "n_cand exceeds bank_size");
   // candidates 0..n-1 in chunks of the scratch capacity
   const int maxp = h->cfg.max_batch_pairs;
   for (int p0 = 0; p0 < n_cand; p0 += maxp) {
     const int np = (n_cand - p0 < maxp) ? n_cand - p0 : maxp;
     k_iota<<<(np + 255) / 256, 256, 0, s>>>(h->d_idx_tmp, np, p0);
     OVN_LAUNCH_CHECK(h);
-    int rc = heads_dispatch(h, d_bank, d_query, h->d_idx_tmp, nullptr,
+    int rc = heads_dispatch(h, d_bank, bank_size, d_query, h->d_idx_tmp, nullptr,
                             np, d_overlap + p0, d_yaw + p0,
                             d_corr ? d_corr + (size_t)p0 * h->cfg.leg_output_width : nullptr, s);
     if (rc != OVN_OK) return rc;
@@ -444,15 +527,45 @@ int ovn_heads_1vsN(ovn_handle* h, const float* d_bank, int64_t bank_size, const 
 int ovn_bank_prepare(ovn_handle* h, const float* d_bank, int64_t bank_capacity, int64_t first, int64_t count,
                      void* stream) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   REQUIRE(h, d_bank != nullptr, "d_bank is NULL");
   REQUIRE(h, bank_capacity > 0 && first >= 0 && count >= 0 && first + count <= bank_capacity, "bad row range");
   if (h->cfg.precision != OVN_PREC_F16_TC || count == 0) return OVN_OK;
   if (!h->weights_ready) OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "ovn_bank_prepare: weights not finalised");
-  return tc_bank_prepare(h, d_bank, bank_capacity, first, count, (cudaStream_t)stream);
+  int rc = tc_bank_prepare(h, d_bank, bank_capacity, first, count, (cudaStream_t)stream);
+  if (rc == OVN_OK) OVN_CUDA(h, cudaEventRecord(h->ev_bank, (cudaStream_t)stream));
+  return rc;
+}
+
+int ovn_check(ovn_handle* h, void* stream) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
+  return check_device_error(h, (cudaStream_t)stream);
+}
+
+int ovn_set_feature_center(ovn_handle* h, const float* h_mu) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
+  if (h->cfg.precision != OVN_PREC_F16_TC) return OVN_OK;
+  if (!h->weights_ready) OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "ovn_set_feature_center: weights not finalised");
+  return tc_set_center(h, h_mu);
+}
+
+int ovn_get_feature_center(ovn_handle* h, float* h_mu, int32_t* is_set) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
+  REQUIRE(h, h_mu && is_set, "NULL pointer");
+  if (h->cfg.precision != OVN_PREC_F16_TC || !h->weights_ready) {
+    for (int c = 0; c < kFeatC; ++c) h_mu[c] = 0.f;
+    *is_set = 0;
+    return OVN_OK;
+  }
+  return tc_get_center(h, h_mu, is_set);
 }
 
 int ovn_bank_release(ovn_handle* h, const float* d_bank) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   if (h->cfg.precision != OVN_PREC_F16_TC) return OVN_OK;
   return tc_bank_release(h, d_bank);
 }
@@ -474,6 +587,7 @@ static int ensure_stage(ovn_handle* h, int64_t n_points, int n_scans) {
 int ovn_encode_clouds_host(ovn_handle* h, const float* h_points, const int64_t* h_offsets, int32_t n_scans,
                            float* h_fv) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   REQUIRE(h, n_scans >= 0, "negative size");
   if (n_scans == 0) return OVN_OK;
   REQUIRE(h, h_points && h_offsets && h_fv, "NULL pointer");
@@ -502,8 +616,8 @@ int ovn_encode_clouds_host(ovn_handle* h, const float* h_points, const int64_t* 
     if (rc == OVN_OK) {
       e = cudaMemcpyAsync(h_fv + (size_t)s0 * Wf * kFeatC, d_fv, (size_t)n * Wf * kFeatC * sizeof(float),
                           cudaMemcpyDeviceToHost, s);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
       if (e != cudaSuccess) { h->last_error = cudaGetErrorString(e); rc = OVN_ERR_CUDA; }
+      else rc = check_device_error(h, s);                 // synchronises s
     }
   }
   cudaFree(d_fv);
@@ -514,47 +628,60 @@ int ovn_query_cloud_vs_bank_host(ovn_handle* h, const float* h_points, int64_t n
                                  int64_t bank_size, const int32_t* h_cand_idx, int32_t n_cand, float* h_overlap,
                                  int32_t* h_yaw, float* h_query_fv) {
   if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   REQUIRE(h, n_points >= 0 && n_cand >= 0, "negative size");
   REQUIRE(h, h_points, "h_points is NULL");
   REQUIRE(h, n_cand == 0 || (d_bank && h_overlap && h_yaw), "NULL pointer");
-  REQUIRE(h, n_cand <= h->cfg.max_batch_pairs || h_cand_idx == nullptr, "n_cand exceeds max_batch_pairs");
+  REQUIRE(h, n_cand == 0 || bank_size > 0, "bank_size must be positive");
+  REQUIRE(h, h_cand_idx != nullptr || n_cand <= bank_size, "n_cand exceeds bank_size");
   if (h->cfg.n_prob_channels != 0)
     OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "ovn_query_cloud_vs_bank_host: semantic channels are not supported here");
+  if (n_cand > h->cfg.max_batch_pairs)
+    OVN_SET_ERR(h, OVN_ERR_CAPACITY, "n_cand=%d exceeds max_batch_pairs=%d", n_cand, h->cfg.max_batch_pairs);
   cudaStream_t s = h->own_stream;
   int rc = ensure_stage(h, n_points, 1);
   if (rc != OVN_OK) return rc;
   const int Wf = h->cfg.leg_output_width;
-  // results staging on device: overlap in d_logit, yaw in d_idx_tmp[max_pairs..]
-  if (n_cand > h->cfg.max_batch_pairs)
-    OVN_SET_ERR(h, OVN_ERR_CAPACITY, "n_cand=%d exceeds max_batch_pairs=%d", n_cand, h->cfg.max_batch_pairs);
-  const int64_t offs[2] = {0, n_points};
+  const int maxp = h->cfg.max_batch_pairs;
+  // pinned staging: [0,64) error flag + the two offsets; then cand idx / overlap / yaw (4 B x max_batch_pairs each).
+  // Everything the device reads or writes asynchronously lives there, so the call has ONE host sync.
+  uint8_t* pin = reinterpret_cast<uint8_t*>(h->h_pinned);
+  int64_t* p_offs = reinterpret_cast<int64_t*>(pin + 16);
+  int32_t* p_idx = reinterpret_cast<int32_t*>(pin + 64);
+  float* p_ov = reinterpret_cast<float*>(pin + 64 + (size_t)maxp * 4);
+  int32_t* p_yaw = reinterpret_cast<int32_t*>(pin + 64 + (size_t)maxp * 8);
+  p_offs[0] = 0; p_offs[1] = n_points;
+  // the bank's operand copies may have been prepared on another stream (ovn_bank_prepare records ev_bank)
+  OVN_CUDA(h, cudaStreamWaitEvent(s, h->ev_bank, 0));
   OVN_CUDA(h, cudaMemcpyAsync(h->d_stage_points, h_points, (size_t)n_points * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
-  OVN_CUDA(h, cudaMemcpyAsync(h->d_stage_offsets, offs, sizeof(offs), cudaMemcpyHostToDevice, s));
-  if (h_cand_idx && n_cand > 0)
-    OVN_CUDA(h, cudaMemcpyAsync(h->d_idx_tmp, h_cand_idx, (size_t)n_cand * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-  OVN_CUDA(h, cudaStreamSynchronize(s));   // offs / caller buffers may be pageable
+  OVN_CUDA(h, cudaMemcpyAsync(h->d_stage_offsets, p_offs, 2 * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  if (h_cand_idx && n_cand > 0) {
+    memcpy(p_idx, h_cand_idx, (size_t)n_cand * sizeof(int32_t));
+    OVN_CUDA(h, cudaMemcpyAsync(h->d_idx_tmp, p_idx, (size_t)n_cand * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  }
   rc = preprocess_batch(h, h->d_stage_points, h->d_stage_offsets, 1, n_points, nullptr, h->d_input, s);
   if (rc != OVN_OK) return rc;
   rc = ovn_leg_forward(h, h->d_input, 1, h->d_query_fv, s);
   if (rc != OVN_OK) return rc;
   if (n_cand > 0) {
-    int32_t* d_yaw = h->d_idx_tmp + h->cfg.max_batch_pairs;
-    if (h_cand_idx) {
-      rc = heads_dispatch(h, d_bank, h->d_query_fv, h->d_idx_tmp, nullptr, n_cand, h->d_logit, d_yaw, nullptr, s);
-    } else {
+    int32_t* d_yaw = h->d_idx_tmp + maxp;
+    if (!h_cand_idx) {
       k_iota<<<(n_cand + 255) / 256, 256, 0, s>>>(h->d_idx_tmp, n_cand, 0);
       OVN_LAUNCH_CHECK(h);
-      rc = heads_dispatch(h, d_bank, h->d_query_fv, h->d_idx_tmp, nullptr, n_cand, h->d_logit, d_yaw, nullptr, s);
     }
+    rc = heads_dispatch(h, d_bank, bank_size, h->d_query_fv, h->d_idx_tmp, nullptr, n_cand, h->d_logit, d_yaw, nullptr, s);
     if (rc != OVN_OK) return rc;
-    OVN_CUDA(h, cudaMemcpyAsync(h_overlap, h->d_logit, (size_t)n_cand * sizeof(float), cudaMemcpyDeviceToHost, s));
-    OVN_CUDA(h, cudaMemcpyAsync(h_yaw, d_yaw, (size_t)n_cand * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    OVN_CUDA(h, cudaMemcpyAsync(p_ov, h->d_logit, (size_t)n_cand * sizeof(float), cudaMemcpyDeviceToHost, s));
+    OVN_CUDA(h, cudaMemcpyAsync(p_yaw, d_yaw, (size_t)n_cand * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   }
   if (h_query_fv)
     OVN_CUDA(h, cudaMemcpyAsync(h_query_fv, h->d_query_fv, (size_t)Wf * kFeatC * sizeof(float), cudaMemcpyDeviceToHost, s));
-  OVN_CUDA(h, cudaStreamSynchronize(s));
-  (void)bank_size;
-  return OVN_OK;
+  rc = check_device_error(h, s);            // the one synchronisation of the call
+  if (n_cand > 0) {                         // results are delivered even on error (poisoned: NaN / INT32_MIN)
+    memcpy(h_overlap, p_ov, (size_t)n_cand * sizeof(float));
+    memcpy(h_yaw, p_yaw, (size_t)n_cand * sizeof(int32_t));
+  }
+  return rc;
 }
 
 }  // extern "C"

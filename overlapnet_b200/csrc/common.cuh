@@ -75,6 +75,9 @@ struct ovn_handle {
   float* d_logit = nullptr;                  // [max_batch_pairs]
   float* d_G = nullptr;                      // [max_batch_pairs][360][360] (fp32 path corr)
   int32_t* d_idx_tmp = nullptr;              // [max_batch_pairs] x2 scratch for 1vsN index lists
+  int32_t* d_idx_san = nullptr;              // [max_batch_pairs] x2 bounds-checked (clamped) copies of the caller's index lists
+  int* d_err = nullptr;                      // device error flag: pipeline barrier time-outs (1xx-8xx), bad indices (9xx)
+  cudaEvent_t ev_bank = nullptr;             // recorded after ovn_bank_prepare: the host entry points (own stream) wait on it
   float* d_query_fv = nullptr;               // [360][128]
   float* d_stage_points = nullptr;           // host-entry staging of clouds
   int64_t cap_stage_points = 0;
@@ -116,6 +119,21 @@ struct ovn_handle {
   } while (0)
 
 namespace ovn {
+
+// Every ABI entry point runs on the device its handle was created on (Engine(device=1)
+// with another current device allocated on the wrong GPU).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const ovn_handle* h) {
+    if (h && cudaGetDevice(&prev) == cudaSuccess && prev != h->device) switched = cudaSetDevice(h->device) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+// error codes written to ovn_handle::d_err by kernels
+constexpr int kErrBadIndex = 900;        // a pair / candidate index outside [0, bank_size)
+constexpr int kErrRowNotPrepared = 901;  // resident bank: the row was never passed to ovn_bank_prepare
 
 // RAII-free profiling helpers: record an event on `s` before / after a launch when enabled
 inline void prof_mark(ovn_handle* h, int kind, cudaStream_t s) {
@@ -161,5 +179,11 @@ int tc_pack_weights(ovn_handle* h);
 int tc_bank_prepare(ovn_handle* h, const float* d_bank, int64_t capacity, int64_t first, int64_t count, cudaStream_t s);
 int tc_bank_release(ovn_handle* h, const float* d_bank);
 void tc_free(ovn_handle* h);
+int tc_set_center(ovn_handle* h, const float* h_mu);
+int tc_get_center(ovn_handle* h, float* h_mu, int32_t* is_set);
+// bounds-checked copies of index lists (d_idx_san): out-of-range entries are clamped and flagged in d_err
+int sanitize_indices(ovn_handle* h, const int32_t* d_in, int n, int64_t limit, int code, int32_t* d_out, cudaStream_t s);
+// read (and clear) the device error flag after the caller has synchronised `s`; maps it to a status
+int check_device_error(ovn_handle* h, cudaStream_t s);
 
 }  // namespace ovn

@@ -90,6 +90,27 @@ class Engine:
   def launch_count(self):
     return int(lib().ovn_launch_count(self._h))
 
+  def check(self):
+    """ovn_check: synchronises the current stream and raises OvnError if a kernel flagged an error
+    since the last check (index out of range, unprepared resident row, pipeline barrier time-out);
+    the affected outputs hold NaN / INT32_MIN."""
+    check(self._h, lib().ovn_check(self._h, self._stream()), 'ovn_check')
+
+  def set_feature_center(self, mu=None):
+    """Fix the per-channel centre of the fp16 operand copies (None = calibrate at first use)."""
+    ptr = None
+    if mu is not None:
+      mu = np.ascontiguousarray(mu, np.float32).reshape(FEAT_C)
+      ptr = mu.ctypes.data_as(C.c_void_p)
+    check(self._h, lib().ovn_set_feature_center(self._h, ptr), 'ovn_set_feature_center')
+
+  def get_feature_center(self):
+    mu = np.zeros(FEAT_C, np.float32)
+    is_set = C.c_int32(0)
+    check(self._h, lib().ovn_get_feature_center(self._h, mu.ctypes.data_as(C.c_void_p), C.byref(is_set)),
+          'ovn_get_feature_center')
+    return mu, bool(is_set.value)
+
   def profile_enable(self, on=True):
     check(self._h, lib().ovn_profile_enable(self._h, int(bool(on))), 'ovn_profile_enable')
 

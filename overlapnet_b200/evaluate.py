@@ -116,7 +116,12 @@ def run_testing(config, precision='f16_tc'):
   for key, default in (('use_depth', True), ('use_normals', True), ('use_class_probabilities', False),
                        ('use_class_probabilities_pca', False), ('use_intensity', False)):
     cfg.setdefault(key, default)                                           # testing.py:97-120 defaults
-  cfg.setdefault('infer_seqs', dir1[0] if dir1 else '')                    # one sequence for all pairs (:216)
+  # testing.py:216 loads the images from the sequence stored in the ground-truth npz (test_dir1[0]) and
+  # ignores config['infer_seqs']; the config value is only a fallback for the old npz format (dir1 == '')
+  if len(dir1) and str(dir1[0]) != '':
+    cfg['infer_seqs'] = str(dir1[0])
+  else:
+    cfg.setdefault('infer_seqs', '')
   if 'imgpath' in cfg:
     cfg['data_root_folder'] = cfg['imgpath']
   infer = Infer(cfg, precision=precision)

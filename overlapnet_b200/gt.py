@@ -61,19 +61,25 @@ def euler_angles_from_rotation_matrix(R):
 
 
 def overlap_yaw_from_clouds(clouds, poses, frame_idx, leg_output_width=360, scans_per_launch=16):
-  """The body of ``com_overlap_yaw`` on in-memory clouds (list of (N,4) float32 arrays): rows
-  [frame_idx, reference_idx, overlap, yaw bin] as float64."""
+  """The body of ``com_overlap_yaw``: rows [frame_idx, reference_idx, overlap, yaw bin] as float64.
+  ``clouds``: list of (N,4) float32 arrays, or of zero-argument callables returning one (read lazily,
+  ``scans_per_launch`` at a time, so a whole KITTI sequence never sits in host memory)."""
   poses = np.asarray(poses, dtype=np.float64)
   n = len(clouds)
   eng = _engine(3.0, -25.0, 64, 900, 50)
-  cur = eng.gt_range(eng.upload_clouds([np.ascontiguousarray(clouds[frame_idx], np.float32)]))[0]
+
+  def get(i):
+    c = clouds[i]
+    return np.ascontiguousarray(c() if callable(c) else c, np.float32)
+
+  cur = eng.gt_range(eng.upload_clouds([get(frame_idx)]))[0]
   current_pose = poses[frame_idx]
   cur_inv = np.linalg.inv(current_pose)
   counts = np.zeros(n, np.int64)
   valid_num = 0
   for s0 in range(0, n, scans_per_launch):
     s1 = min(n, s0 + scans_per_launch)
-    batch = eng.upload_clouds([np.ascontiguousarray(c, np.float32) for c in clouds[s0:s1]])
+    batch = eng.upload_clouds([get(i) for i in range(s0, s1)])
     ref = eng.gt_range(batch, pose_ref=poses[s0:s1], pose_cur_inv=cur_inv)
     c = eng.gt_overlap_count(ref, cur).cpu().numpy()
     counts[s0:s1] = c[:-1]
@@ -95,7 +101,7 @@ def com_overlap_yaw(scan_paths, poses, frame_idx, leg_output_width=360):
   every scan in ``scan_paths`` against scan ``frame_idx``, from the ground-truth ``poses`` (n,4,4).
   Returns the (n, 4) float64 array [current_frame_idx, reference_frame_idx, overlap, yaw]."""
   print('Start to compute ground truth overlap and yaw ...')
-  clouds = [_read_scan(p) for p in scan_paths]
+  clouds = [(lambda p=p: _read_scan(p)) for p in scan_paths]      # streamed like the reference (one scan at a time there)
   mapping = overlap_yaw_from_clouds(clouds, poses, frame_idx, leg_output_width)
   print('Finish generating ground_truth_mapping!')
   return mapping

@@ -123,6 +123,9 @@ class Infer():
     self._fv_as_array = isinstance(value, np.ndarray)
 
   def _set_bank(self, fv):
+    # the resident operand copies are keyed by the storage address: drop them before the old tensor can
+    # be freed (and its address handed to another tensor by the caching allocator)
+    self._engine.bank_release(None)
     self._bank = fv.contiguous()
     self._bank_n = int(fv.shape[0])
     if self._bank_n:
@@ -134,6 +137,7 @@ class Infer():
       cap = max(1024, 2 * (self._bank_n + n))
       nb = torch.empty((cap, self.network_output_size, FEAT_C), dtype=torch.float32, device=self._engine.device)
       nb[:self._bank_n] = self._bank[:self._bank_n]
+      self._engine.bank_release(None)                             # before the old storage is dropped
       self._bank = nb
       if self._bank_n:
         self._engine.bank_prepare(self._bank, 0, self._bank_n)    # new storage: rebuild the resident copies
@@ -169,6 +173,7 @@ class Infer():
     left = torch.where(left < 0, left + n, left)               # numpy-style negative indices
     right = torch.where(right < 0, right + n, right)
     ov, yaw, _ = self._engine.heads(self._bank[:n], left, right)
+    self._engine.check()                                       # deferred device errors -> exception, never garbage
     return ov.cpu().numpy()[:, None], yaw.cpu().numpy().astype(np.int64)
 
   def infer_one(self, filepath1, filepath2):
@@ -186,6 +191,7 @@ class Infer():
 
     fv = self._create_feature_volumes_device(self.filenames)
     ov, yaw, _ = self._engine.heads(fv, torch.tensor([0], dtype=torch.int32), torch.tensor([1], dtype=torch.int32))
+    self._engine.check()
     overlap_out = ov.cpu().numpy()[:, None][0]                 # model_outputs[0][0]
     yaw_out = yaw.cpu().numpy().astype(np.int64)               # 180 - argmax, computed on device
     return overlap_out, yaw_out
@@ -293,4 +299,5 @@ class Infer():
     clouds = [np.fromfile(p, dtype=np.float32).reshape((-1, 4)) for p in (filepath2, filepath1)]
     fv = self.encode_clouds(clouds)
     ov, yaw, _ = self._engine.heads(fv, torch.tensor([0], dtype=torch.int32), torch.tensor([1], dtype=torch.int32))
+    self._engine.check()
     return ov.cpu().numpy(), yaw.cpu().numpy().astype(np.int64)

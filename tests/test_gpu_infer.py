@@ -48,6 +48,13 @@ def dataset(tmp_path_factory):
     np.save(str(seq / 'depth' / ('%06d.npy' % i)), rng)
     np.save(str(seq / 'normal' / ('%06d.npy' % i)), P.gen_normal_map(rng, vert))
   w = N.glorot_weights(4, MODEL, seed=3)
+  # spread the overlaps of the four scans' pairs over (0,1) (tests/test_gpu_network.py explains why)
+  imgs = np.stack([np.concatenate([np.load(str(seq / 'depth' / ('%06d.npy' % i)))[..., None],
+                                   np.load(str(seq / 'normal' / ('%06d.npy' % i)))], -1) for i in range(4)])
+  fvs = N.leg_forward(imgs.astype(np.float32), w, MODEL)
+  li, ri = np.array([1, 0, 0, 1, 3, 1, 2]), np.array([0, 1, 2, 2, 0, 3, 0])   # no self pair: its logit is an outlier
+  _, _, _, z0 = N.heads_forward(fvs[li], fvs[ri], w, MODEL, return_logit=True)
+  w = N.spread_dense(w, z0, target_std=1.5)
   wpath = str(root / 'weights.npz')
   W.save_npz(wpath, w)
   cfg = {'pretrained_weightsfilename': wpath, 'use_depth': True, 'use_normals': True,
