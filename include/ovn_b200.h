@@ -174,6 +174,14 @@ int ovn_heads_1vsN(ovn_handle* h, const float* d_bank, int64_t bank_size, const 
                    const int32_t* d_cand_idx, int32_t n_cand,
                    float* d_overlap, int32_t* d_yaw, float* d_corr, void* stream);
 
+/* Rows [row_lo, row_hi) of the ordered all-pairs matrix of a bank (Infer.infer_multiple_vs_multiple,
+ * infer.py:205-238, with every (first, second) combination; testing.py:237-272): for each row i,
+ * RIGHT = d_bank[i] and LEFT = d_bank[j] for every j < bank_size.  The delta head is not symmetric in
+ * (LEFT, RIGHT), so all ordered pairs are computed.  d_overlap / d_yaw: [row_hi - row_lo][bank_size].
+ * The loop over rows runs inside the library (no per-row host round trip through the caller). */
+int ovn_heads_rows_vs_bank(ovn_handle* h, const float* d_bank, int64_t bank_size, int64_t row_lo, int64_t row_hi,
+                           float* d_overlap, int32_t* d_yaw, void* stream);
+
 /* ---- resident bank (Infer keeps self.feature_volumes across calls, infer.py:113,184-193) ---------
  * The tensor-core heads consume fp16 / hi-lo split copies of the LEFT volumes.  Without this call
  * they are rebuilt from d_bank on every heads call; ovn_bank_prepare builds them once for rows

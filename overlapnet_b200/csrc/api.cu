@@ -524,6 +524,24 @@ int ovn_heads_1vsN(ovn_handle* h, const float* d_bank, int64_t bank_size, const 
   return OVN_OK;
 }
 
+int ovn_heads_rows_vs_bank(ovn_handle* h, const float* d_bank, int64_t bank_size, int64_t row_lo, int64_t row_hi,
+                           float* d_overlap, int32_t* d_yaw, void* stream) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
+  REQUIRE(h, bank_size >= 0 && row_lo >= 0 && row_lo <= row_hi && row_hi <= bank_size, "bad row range");
+  if (row_lo == row_hi || bank_size == 0) return OVN_OK;
+  REQUIRE(h, d_bank && d_overlap && d_yaw, "NULL pointer");
+  REQUIRE(h, bank_size <= INT32_MAX, "bank too large");
+  const size_t vol = (size_t)h->cfg.leg_output_width * kFeatC;
+  for (int64_t i = row_lo; i < row_hi; ++i) {
+    int rc = ovn_heads_1vsN(h, d_bank, bank_size, d_bank + (size_t)i * vol, nullptr, (int32_t)bank_size,
+                            d_overlap + (size_t)(i - row_lo) * bank_size, d_yaw + (size_t)(i - row_lo) * bank_size,
+                            nullptr, stream);
+    if (rc != OVN_OK) return rc;
+  }
+  return OVN_OK;
+}
+
 int ovn_bank_prepare(ovn_handle* h, const float* d_bank, int64_t bank_capacity, int64_t first, int64_t count,
                      void* stream) {
   if (!h) return OVN_ERR_INVALID_ARG;

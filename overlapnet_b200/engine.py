@@ -248,20 +248,38 @@ class Engine:
                                           _ptr(yaw), _ptr(corr), self._stream()), 'ovn_heads_forward')
     return ov, yaw, corr
 
-  def heads_1vsN(self, bank, query, cand_idx=None, n_cand=None, want_corr=False):
-    """RIGHT = query [360,128] for every pair, LEFT = bank[cand_idx] (None = first n_cand rows)."""
+  def heads_1vsN(self, bank, query, cand_idx=None, n_cand=None, want_corr=False, out=None):
+    """RIGHT = query [360,128] for every pair, LEFT = bank[cand_idx] (None = first n_cand rows).
+    ``out`` = (overlap f32 [n], yaw i32 [n]) tensors to write into -- they may live in another GPU's
+    peer-mapped memory (search.py transport 'symm'): the kernels that finish a pair store there directly."""
     if cand_idx is not None:
       ci = cand_idx.to(device=self.device, dtype=torch.int32).contiguous()
       n = ci.numel()
     else:
       ci = None
       n = int(bank.shape[0] if n_cand is None else n_cand)
-    ov = torch.empty((n,), dtype=torch.float32, device=self.device)
-    yaw = torch.empty((n,), dtype=torch.int32, device=self.device)
+    if out is not None:
+      ov, yaw = out
+      assert ov.numel() == n and yaw.numel() == n and ov.dtype == torch.float32 and yaw.dtype == torch.int32
+      assert ov.is_contiguous() and yaw.is_contiguous()
+    else:
+      ov = torch.empty((n,), dtype=torch.float32, device=self.device)
+      yaw = torch.empty((n,), dtype=torch.int32, device=self.device)
     corr = torch.empty((n, self.Wf), dtype=torch.float32, device=self.device) if want_corr else None
     check(self._h, lib().ovn_heads_1vsN(self._h, _ptr(bank), int(bank.shape[0]), _ptr(query), _ptr(ci), n, _ptr(ov),
                                        _ptr(yaw), _ptr(corr), self._stream()), 'ovn_heads_1vsN')
     return ov, yaw, corr
+
+  def heads_rows_vs_bank(self, bank, row_lo, row_hi):
+    """Rows [row_lo, row_hi) of the ordered all-pairs matrix of ``bank`` (RIGHT = bank[i], LEFT = every
+    row): (overlap [rows, n] f32, yaw [rows, n] i32).  One C-ABI call; the row loop runs in the library."""
+    n = int(bank.shape[0])
+    rows = int(row_hi) - int(row_lo)
+    ov = torch.empty((rows, n), dtype=torch.float32, device=self.device)
+    yaw = torch.empty((rows, n), dtype=torch.int32, device=self.device)
+    check(self._h, lib().ovn_heads_rows_vs_bank(self._h, _ptr(bank), n, int(row_lo), int(row_hi), _ptr(ov), _ptr(yaw),
+                                               self._stream()), 'ovn_heads_rows_vs_bank')
+    return ov, yaw
 
   def bank_prepare(self, bank, first=0, count=None):
     """Keep the tensor-core operand copies of bank rows [first, first+count) resident: later heads

@@ -73,7 +73,10 @@ class LoopClosureDetector:
     reference_idx = gate_candidates(idx, traj, self.traj_length, ellipse, self.inactive_time_thres,
                                     self.inactive_dist_thres)
     if len(reference_idx) > 0:
-      overlaps, _ = self.infer.infer_multiple(idx, reference_idx)
+      res = self.infer.infer_multiple(idx, reference_idx)
+      if res is None:                      # ShardedInfer: ranks other than the source only follow along
+        return None
+      overlaps, _ = res
       if np.max(overlaps) > self.overlap_thres:
         return int(reference_idx[np.argmax(overlaps)])
       return None

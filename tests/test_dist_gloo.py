@@ -80,3 +80,73 @@ def test_sharded_search_world2_matches_single_process(tmp_path):
   for i in range(n_total):
     o, y = _cheap_heads(torch.from_numpy(bank), torch.from_numpy(bank[i]))
     assert np.array_equal(got['ap_ov'][i], o.numpy()) and np.array_equal(got['ap_yaw'][i], y.numpy())
+
+
+# ---- the growing, sharded loop-closure bank (search.ShardedBank) under gloo ----------------------
+def _bank_worker(rank, world, port, out_path):
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  from overlapnet_b200.search import ShardedBank
+  from overlapnet_b200 import lcd
+  from conftest import GOLDEN
+  g = np.load(os.path.join(GOLDEN, 'lcd_demo3.npz'))
+  W, C = 12, 4
+  rng = np.random.default_rng(0)
+  vols = np.abs(rng.standard_normal((len(g['traj']), W, C))).astype(np.float32)     # "encoded" frame i
+  local = []                                                                       # this rank's rows
+
+  def heads(local_rows, q):
+    bank = torch.from_numpy(np.stack([local[int(r)] for r in local_rows.tolist()]))
+    return _cheap_heads(bank, q)
+
+  sb = ShardedBank(lambda fid: torch.from_numpy(vols[fid]), lambda fv: local.append(fv.numpy().copy()), heads,
+                   (W, C), torch.device('cpu'))
+
+  class Adapter:                       # what lcd.LoopClosureDetector needs of an Infer
+    def __init__(self):
+      self.results = []
+
+    def infer_multiple(self, idx, refs):
+      res = sb.step(idx, refs)
+      if res is None:
+        if rank != 0 and len(refs) > 0:
+          return np.zeros(len(refs), np.float32), np.zeros(len(refs), np.int64)    # non-source ranks only follow
+        return None
+      ov, yaw = res
+      self.results.append((idx, list(map(int, refs)), ov.numpy().copy(), yaw.numpy().copy()))
+      return ov.numpy(), yaw.numpy()
+
+  ad = Adapter()
+  det = lcd.LoopClosureDetector(ad, overlap_thres=2.0)       # never "finds" one: every frame is scored and appended
+  for i in range(260):
+    det.step(i, g['traj'][i], g['covs'][i])
+  assert len(local) == len(range(rank, 260, world))          # frame i lives on rank i % world
+  for k, v in enumerate(local):
+    assert np.array_equal(v, vols[rank + k * world])
+  if rank == 0:
+    np.savez(out_path, n=len(ad.results), idx=np.array([r[0] for r in ad.results]),
+             refs=np.concatenate([np.array(r[1]) for r in ad.results]),
+             ov=np.concatenate([r[2] for r in ad.results]), yaw=np.concatenate([r[3] for r in ad.results]),
+             offs=np.cumsum([0] + [len(r[1]) for r in ad.results]))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_sharded_growing_bank_world2_matches_single_process(tmp_path):
+  """Frames 0..259 of the golden LCD run through ShardedBank on 2 ranks: every scored candidate gets
+  the value a single process computes from the full bank, in the caller's candidate order."""
+  from conftest import GOLDEN
+  out = str(tmp_path / 'bank.npz')
+  mp.spawn(_bank_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+  got = np.load(out)
+  g = np.load(os.path.join(GOLDEN, 'lcd_demo3.npz'))
+  rng = np.random.default_rng(0)
+  vols = np.abs(rng.standard_normal((len(g['traj']), 12, 4))).astype(np.float32)
+  assert got['n'] > 20
+  for k in range(int(got['n'])):
+    idx = int(got['idx'][k])
+    refs = got['refs'][got['offs'][k]:got['offs'][k + 1]]
+    ov, yaw = _cheap_heads(torch.from_numpy(vols[refs]), torch.from_numpy(vols[idx]))
+    assert np.array_equal(got['ov'][got['offs'][k]:got['offs'][k + 1]], ov.numpy())
+    assert np.array_equal(got['yaw'][got['offs'][k]:got['offs'][k + 1]], yaw.numpy())

@@ -77,3 +77,44 @@ def test_driver_decisions_and_bank_protocol():
   assert all(len(c[1]) == 0 for c in stub.calls[:100])
   assert found and all(found[i] == i - 200 for i in found)
   assert min(found) >= 200
+
+
+def _golden_overlap(idx, ref):
+  """tools/make_golden_lcd.py:overlap_field (the seeded overlap field the golden run used)."""
+  if ref == idx - 200:
+    return 0.9
+  h = (idx * 7919 + ref * 104729) % 1000
+  return 0.45 if h < 12 else 0.001 * (h % 250)
+
+
+class FieldInfer:
+  def __init__(self):
+    self.calls = []
+
+  def infer_multiple(self, idx, refs):
+    refs = [int(r) for r in refs]
+    self.calls.append((int(idx), refs))
+    if not refs:
+      return None
+    return np.array([_golden_overlap(idx, r) for r in refs], np.float32), np.zeros(len(refs), np.int64)
+
+
+def test_driver_matches_the_reference_run():
+  """Pinned to the reference itself: tests/golden/lcd_demo3.npz holds what demo3_lcd.py's own
+  get_predictions / get_cov_ellipse (executed by tools/make_golden_lcd.py) asked of Infer for 300
+  frames and which loop closures they reported."""
+  import os
+  from conftest import GOLDEN
+  g = np.load(os.path.join(GOLDEN, 'lcd_demo3.npz'))
+  inf = FieldInfer()
+  det = lcd.LoopClosureDetector(inf)
+  dec = []
+  for i in range(len(g['traj'])):
+    r = det.step(i, g['traj'][i], g['covs'][i])
+    dec.append(-1 if r is None else int(r))
+  assert np.array_equal(np.array(dec), g['decisions'])
+  assert [c[0] for c in inf.calls] == g['call_idx'].tolist()
+  offs = g['call_offsets']
+  for k, (_, refs) in enumerate(inf.calls):
+    assert refs == g['call_refs'][offs[k]:offs[k + 1]].tolist()
+  assert (g['decisions'] >= 0).sum() > 50 and len(g['call_refs']) > 500      # the golden run is not trivial
