@@ -76,8 +76,15 @@ struct TcState {
   // fp16 rounding error of the (coherently re-used) volumes.  mu is calibrated once (first bank rows /
   // first RIGHT volume seen) or set through ovn_set_feature_center; values are fp16-representable.
   float* mu = nullptr;          // [128] device
-  float mu_host[CF] = {};
   bool mu_set = false;
+  // The same trick one and two layers further on: c_conv2 and c_conv3 are linear in their inputs, so
+  // o1 and x3 are stored as fp16(x - mean[channel]) and the mean's image under the layer is folded into
+  // that layer's bias (b2eff / b3eff).  Calibrated on the first pairs the handle scores.
+  float* mu_o1 = nullptr;       // [64]
+  float* mu_x3 = nullptr;       // [128]
+  float* b2base = nullptr;      // c_conv2 bias + c_conv1 bias pushed through W2
+  float* b3eff = nullptr;       // c_conv3 bias + mu_x3 pushed through the fp16 W3
+  bool act_set = false;
   int64_t rows_pad = 0;
 };
 
@@ -159,6 +166,7 @@ struct K4Smem {
   uint8_t epi[K4_TILES][4][32 * 128];   // [tile][epilogue warp]: 32 fp16 output rows staged for the transposed store
   uint64_t a_full[K4_STAGES], a_empty[K4_STAGES], b_full[K4_BGROUPS], b_empty[K4_BGROUPS];
   uint64_t d_full, d_empty[K4_TILES], l_full, l_empty, rw_full[2], rw_empty[2];
+  float mu_o1[64];                      // per-channel centre subtracted before the fp16 rounding of o1
   uint32_t tmem_base;
 };
 
@@ -194,7 +202,8 @@ __device__ long long g_k4_trace[8][64][4];
 // memory and stores whole 128 B lines, and hands the accumulator back tile by tile.
 __global__ void __launch_bounds__(K4_THREADS, 1)
 k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_idx, const __half* __restrict__ R16,
-                 int r_per_pair, const __half* __restrict__ W1p, __half* __restrict__ o1, int n_pairs, int* __restrict__ err) {
+                 int r_per_pair, const __half* __restrict__ W1p, const float* __restrict__ mu_o1, __half* __restrict__ o1,
+                 int n_pairs, int* __restrict__ err) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   K4Smem& S = *reinterpret_cast<K4Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -211,6 +220,7 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_i
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(&S.tmem_base, 512);
+  if (tid >= 64 && tid < 128) S.mu_o1[tid - 64] = mu_o1[tid - 64];
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -370,7 +380,8 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_i
             for (int j = 0; j < 4; ++j) {
               const uint32_t a = c ? v1[h8 * 8 + 2 * j] : v0[h8 * 8 + 2 * j];
               const uint32_t b = c ? v1[h8 * 8 + 2 * j + 1] : v0[h8 * 8 + 2 * j + 1];
-              __half2 hh = __floats2half2_rn(__uint_as_float(a), __uint_as_float(b));
+              const float2 m = *reinterpret_cast<const float2*>(&S.mu_o1[c * 32 + h8 * 8 + 2 * j]);   // broadcast LDS
+              __half2 hh = __floats2half2_rn(__uint_as_float(a) - m.x, __uint_as_float(b) - m.y);
               pk[j] = *reinterpret_cast<uint32_t*>(&hh);
             }
             *reinterpret_cast<uint4*>(row + (((c * 4 + h8) ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -699,7 +710,7 @@ constexpr int C2_STAGES = 3, C2_TILE_BYTES = 128 * 128;
 
 struct C2Smem {
   uint8_t st[C2_STAGES][4][C2_TILE_BYTES];     // [A tile 0][A tile 1][W2 hi tile][W2 lo tile]
-  float bias[128];
+  float bias[128], mu[128];
   uint64_t full[C2_STAGES], empty[C2_STAGES], d_full[2], d_empty[2];
   uint32_t tmem_base;
 };
@@ -711,7 +722,8 @@ struct C2Smem {
 // runs into its bounded barrier wait and the error flag is raised (tests/test_gpu_errors.py).
 __global__ void __launch_bounds__(G_THREADS, 1)
 k_conv2_sw_tc(const __half* __restrict__ o1, const __half* __restrict__ W2s, const float* __restrict__ bias2,
-              __half* __restrict__ x3, int64_t out_pitch, int64_t M, int n_iter, int fault, int* __restrict__ err) {
+              const float* __restrict__ mu_x3, __half* __restrict__ x3, int64_t out_pitch, int64_t M, int n_iter, int fault,
+              int* __restrict__ err) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   C2Smem& S = *reinterpret_cast<C2Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -720,7 +732,7 @@ k_conv2_sw_tc(const __half* __restrict__ o1, const __half* __restrict__ W2s, con
     for (int b = 0; b < 2; ++b) { mbar_init(&S.d_full[b], 1); mbar_init(&S.d_empty[b], 4); }
     mbar_fence_init();
   }
-  if (tid < 128) S.bias[tid] = bias2[tid];
+  if (tid < 128) { S.bias[tid] = bias2[tid]; S.mu[tid] = mu_x3[tid]; }
   if (warp == 2) tmem_alloc(&S.tmem_base, 512);
   fence_before_sync();
   __syncthreads();
@@ -803,8 +815,8 @@ k_conv2_sw_tc(const __half* __restrict__ o1, const __half* __restrict__ W2s, con
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int c = c0 + j8 * 8 + 2 * j;
-                __half2 hh = __floats2half2_rn(fmaxf(__uint_as_float(v[j8 * 8 + 2 * j]) + S.bias[c], 0.f),
-                                               fmaxf(__uint_as_float(v[j8 * 8 + 2 * j + 1]) + S.bias[c + 1], 0.f));
+                __half2 hh = __floats2half2_rn(fmaxf(__uint_as_float(v[j8 * 8 + 2 * j]) + S.bias[c], 0.f) - S.mu[c],
+                                               fmaxf(__uint_as_float(v[j8 * 8 + 2 * j + 1]) + S.bias[c + 1], 0.f) - S.mu[c + 1]);
                 pk[j] = *reinterpret_cast<uint32_t*>(&hh);
               }
               *reinterpret_cast<uint4*>(x3 + ((size_t)(c0 / 8 + j8) * out_pitch + m) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -1527,6 +1539,67 @@ k_corr_finalize(const float* __restrict__ part, float* __restrict__ corr_out, in
   }
 }
 
+// ---- calibration of the o1 / x3 centres (runs once per handle, on the first pairs it scores) --------
+// per-channel mean of o1 over rows [0, M): o1 tiles [m/128][15 di][128][64 swizzled]; one block, fixed order
+__global__ void __launch_bounds__(1024)
+k_o1_channel_mean(const __half* __restrict__ o1, int64_t M, float* __restrict__ mu) {
+  __shared__ float part[16][64];
+  const int o = threadIdx.x & 63, g = threadIdx.x >> 6;            // 16 row groups
+  float acc = 0.f;
+  for (int64_t m = g; m < M; m += 16)
+    for (int di = 0; di < S15; ++di) acc += __half2float(o1[o1_chunk_offset(m, di, o >> 3) + (o & 7)]);
+  part[g][o] = acc;
+  __syncthreads();
+  if (g == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 16; ++k) t += part[k][o];
+    mu[o] = t / (float)(M * S15);
+  }
+}
+
+// per-channel mean of x3 over rows [0, M): planes [16][pitch][8]
+__global__ void __launch_bounds__(1024)
+k_x3_channel_mean(const __half* __restrict__ x3, int64_t pitch, int64_t M, float* __restrict__ mu) {
+  __shared__ float part[8][128];
+  const int n = threadIdx.x & 127, g = threadIdx.x >> 7;
+  float acc = 0.f;
+  for (int64_t m = g; m < M; m += 8) acc += __half2float(x3[((size_t)(n >> 3) * pitch + m) * 8 + (n & 7)]);
+  part[g][n] = acc;
+  __syncthreads();
+  if (g == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += part[k][n];
+    mu[n] = t / (float)M;
+  }
+}
+
+// b2eff[n] = b2base[n] + sum_{di,o} mu_o1[o] W2[di][o][n]      (c_conv2 is linear: generateNet.py:102-106)
+__global__ void __launch_bounds__(128)
+k_fold_bias2(const float* __restrict__ b2base, const float* __restrict__ mu_o1, const float* __restrict__ W2,
+             float* __restrict__ b2eff) {
+  const int n = threadIdx.x;
+  float acc = b2base[n];
+  for (int di = 0; di < S15; ++di)
+    for (int o = 0; o < 64; ++o) acc = fmaf(mu_o1[o], W2[((size_t)di * 64 + o) * 128 + n], acc);
+  b2eff[n] = acc;
+}
+
+// b3eff[m] = b3[m] + sum_{tap,n} mu_x3[n] W3[tap][n][m] with the EXACT fp32 weights: the tensor path then
+// computes  sum (x3 - mu) W3_f16 + sum mu W3_f32 = sum x3 W3_f32 - sum (x3 - mu) dW3,  i.e. the fp16
+// rounding of W3 only acts on the centred fluctuation of x3.  Without this its effect was a nearly
+// pair-independent logit offset (a static perturbation times a non-negative input of stable mean):
+// the largest single term of the error budget on the Infer parity test (profiles/r2_precision_budget.txt).
+__global__ void __launch_bounds__(256)
+k_fold_bias3(const float* __restrict__ b3, const float* __restrict__ mu_x3, const float* __restrict__ W3,
+             float* __restrict__ b3eff) {
+  const int m = threadIdx.x;
+  float acc = b3[m];
+  for (int tap = 0; tap < 9; ++tap)
+    for (int n = 0; n < 128; ++n)
+      acc = fmaf(mu_x3[n], W3[((size_t)tap * 128 + n) * 256 + m], acc);
+  b3eff[m] = acc;
+}
+
 // Dense bias + sigmoid: fixed-order reduction of the per-row partial sums of one pair
 __global__ void __launch_bounds__(256)
 k_dense_finalize(const float* __restrict__ partial, const float* __restrict__ bd, int rows_per_pair,
@@ -1621,7 +1694,8 @@ void tc_free(ovn_handle* h) {
   TcState* t = h->tc;
   if (!t) return;
   void* bufs[] = {t->w1p, t->w2p, t->w3p, t->b2eff,
-                  t->l16, t->r16, t->o1, t->x3, t->partial, t->mu, t->lc, t->rc, t->corr_part};
+                  t->l16, t->r16, t->o1, t->x3, t->partial, t->mu, t->lc, t->rc, t->corr_part,
+                  t->mu_o1, t->mu_x3, t->b2base, t->b3eff};
   for (void* b : bufs) if (b) cudaFree(b);
   for (int l = 0; l < kMaxLegLayers; ++l) {
     if (t->wleg[l]) cudaFree(t->wleg[l]);
@@ -1708,6 +1782,12 @@ int tc_pack_weights(ovn_handle* h) {
   }
   int rc;
   if ((rc = upload_vec(h, &t->b2eff, b2e)) != OVN_OK) return rc;
+  if ((rc = upload_vec(h, &t->b2base, b2e)) != OVN_OK) return rc;
+  if ((rc = upload_vec(h, &t->b3eff, w3.bias)) != OVN_OK) return rc;
+  OVN_CUDA(h, cudaMalloc(&t->mu_o1, 64 * sizeof(float)));
+  OVN_CUDA(h, cudaMemset(t->mu_o1, 0, 64 * sizeof(float)));
+  OVN_CUDA(h, cudaMalloc(&t->mu_x3, 128 * sizeof(float)));
+  OVN_CUDA(h, cudaMemset(t->mu_x3, 0, 128 * sizeof(float)));
   if ((rc = upload_vec(h, &t->w1p, p1)) != OVN_OK) return rc;
   if ((rc = upload_vec(h, &t->w2p, p2)) != OVN_OK) return rc;
   if ((rc = upload_vec(h, &t->w3p, p3)) != OVN_OK) return rc;
@@ -1976,6 +2056,9 @@ int tc_set_center(ovn_handle* h, const float* h_mu) {
     OVN_SET_ERR(h, OVN_ERR_INVALID_ARG, "ovn_set_feature_center: release the resident bank first (its operand copies "
                 "were built with the previous centre)");
   OVN_CUDA(h, cudaDeviceSynchronize());
+  t->act_set = false;                // the o1 / x3 centres are re-calibrated with the new operands
+  OVN_CUDA(h, cudaMemset(t->mu_o1, 0, 64 * sizeof(float)));
+  OVN_CUDA(h, cudaMemset(t->mu_x3, 0, 128 * sizeof(float)));
   if (!h_mu) {                       // back to "calibrate at first use"
     t->mu_set = false;
     OVN_CUDA(h, cudaMemset(t->mu, 0, CF * sizeof(float)));
@@ -2038,20 +2121,47 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query, c
     }
     const int64_t units = (int64_t)np * NB;
     const int grid4 = units < h->sm_count ? (int)units : h->sm_count;
-    prof_mark(h, PROF_DELTA, s);
-    k_delta_conv1_tc<<<grid4, K4_THREADS, sizeof(K4Smem), s>>>(l16, lidx, t->r16, d_query ? 0 : 1, t->w1p, t->o1, np, h->d_err);
-    prof_mark(h, PROF_DELTA, s);
-    OVN_LAUNCH_CHECK(h);
     const int64_t M = (int64_t)np * PAIR_ROWS;
     const int n_iter2 = (int)((M + 255) / 256);
+    const int grid2 = n_iter2 < h->sm_count ? n_iter2 : h->sm_count;
+    if (!t->act_set) {
+      // One-time calibration of the o1 / x3 centres on (at most 8 of) the first pairs this handle scores:
+      // c_conv1 with centre 0 -> channel means of o1 -> fold into b2eff; c_conv1 again (centred) + c_conv2
+      // with centre 0 -> channel means of x3 -> fold into b3eff.  Everything on the stream, no host sync.
+      const int nc = np < 8 ? np : 8;
+      const int64_t Mc = (int64_t)nc * PAIR_ROWS;
+      const int n_it_c = (int)((Mc + 255) / 256);
+      const int64_t uc = (int64_t)nc * NB;
+      const int g4c = uc < h->sm_count ? (int)uc : h->sm_count;
+      k_delta_conv1_tc<<<g4c, K4_THREADS, sizeof(K4Smem), s>>>(l16, lidx, t->r16, d_query ? 0 : 1, t->w1p, t->mu_o1, t->o1, nc, h->d_err);
+      OVN_LAUNCH_CHECK(h);
+      k_o1_channel_mean<<<1, 1024, 0, s>>>(t->o1, Mc, t->mu_o1);
+      OVN_LAUNCH_CHECK(h);
+      k_fold_bias2<<<1, 128, 0, s>>>(t->b2base, t->mu_o1, h->d_w[base + 1], t->b2eff);
+      OVN_LAUNCH_CHECK(h);
+      k_delta_conv1_tc<<<g4c, K4_THREADS, sizeof(K4Smem), s>>>(l16, lidx, t->r16, d_query ? 0 : 1, t->w1p, t->mu_o1, t->o1, nc, h->d_err);
+      OVN_LAUNCH_CHECK(h);
+      k_conv2_sw_tc<<<n_it_c < h->sm_count ? n_it_c : h->sm_count, G_THREADS, sizeof(C2Smem), s>>>(
+          t->o1, t->w2p, t->b2eff, t->mu_x3, t->x3, t->rows_pad, Mc, n_it_c, 0, h->d_err);
+      OVN_LAUNCH_CHECK(h);
+      k_x3_channel_mean<<<1, 1024, 0, s>>>(t->x3, t->rows_pad, Mc, t->mu_x3);
+      OVN_LAUNCH_CHECK(h);
+      k_fold_bias3<<<1, 256, 0, s>>>(h->d_b[base + 2], t->mu_x3, h->d_w[base + 2], t->b3eff);
+      OVN_LAUNCH_CHECK(h);
+      t->act_set = true;
+    }
+    prof_mark(h, PROF_DELTA, s);
+    k_delta_conv1_tc<<<grid4, K4_THREADS, sizeof(K4Smem), s>>>(l16, lidx, t->r16, d_query ? 0 : 1, t->w1p, t->mu_o1, t->o1, np, h->d_err);
+    prof_mark(h, PROF_DELTA, s);
+    OVN_LAUNCH_CHECK(h);
     prof_mark(h, PROF_CONV2, s);
-    k_conv2_sw_tc<<<n_iter2 < h->sm_count ? n_iter2 : h->sm_count, G_THREADS, sizeof(C2Smem), s>>>(
-        t->o1, t->w2p, t->b2eff, t->x3, t->rows_pad, M, n_iter2, inject_fault ? 1 : 0, h->d_err);
+    k_conv2_sw_tc<<<grid2, G_THREADS, sizeof(C2Smem), s>>>(
+        t->o1, t->w2p, t->b2eff, t->mu_x3, t->x3, t->rows_pad, M, n_iter2, inject_fault ? 1 : 0, h->d_err);
     prof_mark(h, PROF_CONV2, s);
     OVN_LAUNCH_CHECK(h);
     prof_mark(h, PROF_CONV3, s);
-    k_conv3_resident_tc<<<n_iter2 < h->sm_count ? n_iter2 : h->sm_count, G_THREADS, sizeof(C3Smem), s>>>(
-        t->x3, t->rows_pad, t->w3p, h->d_b[base + 2], M, n_iter2, h->d_w[base + 3], t->partial, h->d_err);
+    k_conv3_resident_tc<<<grid2, G_THREADS, sizeof(C3Smem), s>>>(
+        t->x3, t->rows_pad, t->w3p, t->b3eff, M, n_iter2, h->d_w[base + 3], t->partial, h->d_err);
     prof_mark(h, PROF_CONV3, s);
     OVN_LAUNCH_CHECK(h);
     k_dense_finalize<<<np, 256, 0, s>>>(t->partial, h->d_b[base + 3], PAIR_ROWS, d_overlap + p0, h->d_err);

@@ -116,7 +116,7 @@ def test_lcd_on_growing_gpu_bank_matches_reference_semantics(dataset):
   log, found = run_lcd(inf)
   assert len(inf.feature_volumes) == N_FRAMES                   # one appended volume per frame, in order
   scored = sorted(log)
-  assert scored and min(scored) >= LAP and len(scored) >= 20    # candidates only exist once the loop closes
+  assert scored and min(scored) >= 150 and len(scored) >= 20    # candidates only exist once the loop closes (100 frames + 50 m)
   # oracle: InferRef fed with exactly the frames involved in a few scored queries
   ref = InferRef(copy.deepcopy(cfg), w)
   n_checked = 0

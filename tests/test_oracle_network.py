@@ -92,3 +92,28 @@ def test_readout_first_max_and_range():
   corr[2, [10, 200]] = 1  # tie -> first maximum (np.argmax)
   _, yaw = N.readout(np.zeros(3), corr)
   assert yaw.tolist() == [180, -179, 170]
+
+
+def test_heads_match_independent_einsum_restatement():
+  """tests/golden/heads_pair_einsum.npz: one full-size pair (both orderings) through an independent
+  NumPy-einsum restatement of the two heads (tools/make_golden_heads.py).  The network oracle stays
+  'parity unpinned' by the reference; this catches regressions of oracle/network.py."""
+  import os
+  import sys
+  from conftest import GOLDEN, ROOT
+  sys.path.insert(0, os.path.join(ROOT, 'tools'))
+  import make_golden_heads as G
+  g = np.load(os.path.join(GOLDEN, 'heads_pair_einsum.npz'))
+  w, L, R = G.inputs()
+  for tag, (l, r) in (('lr_', (L, R)), ('rl_', (R, L))):
+    acts, z, ov = N.delta_head(l[None, None], r[None, None], w, G.MODEL, return_all=True)
+    o1, o2, o3 = acts[0][0], acts[1][0], acts[2][0]
+    assert abs(float(z[0, 0]) - float(g[tag + 'logit'])) <= 1e-10 * max(1.0, abs(float(g[tag + 'logit'])))
+    assert abs(float(ov[0, 0]) - float(g[tag + 'overlap'])) <= 1e-12
+    for name, val in (('o1_sum', o1.sum()), ('o1_abs', np.abs(o1).sum()), ('o2_sum', o2.sum()), ('o3_sum', o3.sum())):
+      assert abs(val - float(g[tag + name])) <= 1e-9 * abs(float(g[tag + name]))
+    assert np.allclose(o1[[0, 17, 359], [0, 5, 23], [0, 31, 63]], g[tag + 'o1_probe'], rtol=1e-10, atol=1e-12)
+    assert np.allclose(o2[[0, 11, 23], [0, 7, 23], [0, 64, 127]], g[tag + 'o2_probe'], rtol=1e-10, atol=1e-12)
+    corr = N.correlation_head(l[None, None], r[None, None])[0]
+    assert np.allclose(corr, g[tag + 'corr'], rtol=1e-11, atol=1e-9)
+    assert 180 - int(np.argmax(corr)) == int(g[tag + 'yaw'])

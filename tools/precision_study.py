@@ -73,23 +73,34 @@ def emu_logit(L, R, w, v):
   o1 = torch.einsum('ijdc,dco->ijo', dd, w1[0])
   if not v.get('fold_b1', True):
     o1 = o1 + b1
-  if v.get('o1_16', True):
+  if v.get('o1_center', False):               # fp16(o1 - mean per channel): c_conv2 is linear, the mean folds into its bias
+    mo = h(o1.mean((0, 1)))
+    o1 = h(o1 - mo) + mo
+  elif v.get('o1_16', True):
     o1 = h(o1)
-  elif v.get('o1_hilo', False):
-    pass
   w2 = h(W2) if v.get('w2_16', True) else W2
   # x3[ib, jb, n] = relu(b2eff + sum_{di, o} o1[15 ib + di, jb, o] W2[di, 0, o, n])
   oo = o1.reshape(24, 15, 24, 64)
   b2eff = b2 + (torch.einsum('o,don->n', b1, W2[:, 0]) if v.get('fold_b1', True) else 0)
   b2eff = b2eff.to(torch.float32).to(torch.float64)
   x3 = torch.relu(torch.einsum('idjo,don->ijn', oo, w2[:, 0]) + b2eff)
-  if v.get('x3_16', True):
+  x3_mean = None
+  if v.get('x3_center', False):               # fp16(x3 - mean per channel): folds into the c_conv3 bias
+    mx = h(x3.mean((0, 1)))
+    if v.get('w3_fold_exact', False):         # the mean's image under c_conv3 is folded with the fp32 weights
+      x3_mean = mx
+      x3 = h(x3 - mx)
+    else:
+      x3 = h(x3 - mx) + mx
+  elif v.get('x3_16', True):
     x3 = h(x3)
   elif v.get('x3_hilo', False):
     a, b = hilo(x3)
     x3 = a + b
   w3 = h(W3) if v.get('w3_16', True) else W3
   y = F.conv2d(x3.permute(2, 0, 1)[None], w3.permute(3, 2, 0, 1).contiguous(), b3)
+  if x3_mean is not None:
+    y = y + torch.einsum('n,yxnm->m', x3_mean, W3)[None, :, None, None]
   y = torch.relu(y)[0].permute(1, 2, 0).reshape(-1)          # Flatten (H, W, C)
   return float(y @ Wd[:, 0] + bd[0])
 
