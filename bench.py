@@ -236,7 +236,6 @@ def main():
   dev = torch.device('cuda', local)
   if world > 1:
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-    os.environ.setdefault('NCCL_DEBUG', 'WARN')            # keep rank 0's stdout to the one JSON line
     dist.init_process_group('nccl', device_id=dev)
 
   def timed(fn, steps, warmup):

@@ -208,11 +208,18 @@ int ovn_check(ovn_handle* h, void* stream);
  * DeltaLayer only sees |l - r| (generateNet.py:59), which is invariant to a common per-channel offset:
  * the fp16 operand copies of the volumes are stored as fp16(x - mu[c]), which shrinks their rounding
  * error (measured: 3x on leg outputs, profiles/r2_precision_budget.txt).  mu is calibrated automatically
- * on the first volumes the handle sees (first ovn_bank_prepare rows, else the first RIGHT volume) and
+ * on the first volume the handle sees (first ovn_bank_prepare row, else the first RIGHT volume) and
  * then frozen until ovn_finalize_weights; ovn_set_feature_center(h, mu[128]) fixes it explicitly
  * (NULL = back to automatic; not allowed while a bank is resident).  No effect for precision fp32. */
 int ovn_set_feature_center(ovn_handle* h, const float* h_mu);
 int ovn_get_feature_center(ovn_handle* h, float* h_mu /* [128] */, int32_t* is_set);
+/* The same offset trick is applied to the two intermediate images (o1, x3: c_conv2 and c_conv3 are
+ * linear, the mean's image is folded into the layer's bias with exact fp32 weights).  All three centres are
+ * derived from ONE feature volume V0 with fixed summation orders: mu = channel means of V0, the o1 / x3
+ * centres = channel means over the canonical pair (V0, V0 rolled by half a turn).  V0 is the first volume
+ * the handle sees, or the one given here: ovn_calibrate(h, d_volume [360][128]) makes the calibration
+ * explicit, so that handles on different GPUs (a sharded bank) produce bit-identical results. */
+int ovn_calibrate(ovn_handle* h, const float* d_volume, void* stream);
 
 /* ---- host-buffer convenience entry points (what a non-CUDA caller binds; bench.py e2e) ------ */
 /* Raw clouds on the host -> feature volumes on the host. */

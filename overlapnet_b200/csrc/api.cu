@@ -569,6 +569,15 @@ int ovn_set_feature_center(ovn_handle* h, const float* h_mu) {
   return tc_set_center(h, h_mu);
 }
 
+int ovn_calibrate(ovn_handle* h, const float* d_volume, void* stream) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
+  REQUIRE(h, d_volume != nullptr, "d_volume is NULL");
+  if (h->cfg.precision != OVN_PREC_F16_TC) return OVN_OK;
+  if (!h->weights_ready) OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "ovn_calibrate: weights not finalised");
+  return tc_calibrate(h, d_volume, (cudaStream_t)stream);
+}
+
 int ovn_get_feature_center(ovn_handle* h, float* h_mu, int32_t* is_set) {
   if (!h) return OVN_ERR_INVALID_ARG;
   DeviceGuard guard(h);

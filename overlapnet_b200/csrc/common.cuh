@@ -181,6 +181,7 @@ int tc_bank_release(ovn_handle* h, const float* d_bank);
 void tc_free(ovn_handle* h);
 int tc_set_center(ovn_handle* h, const float* h_mu);
 int tc_get_center(ovn_handle* h, float* h_mu, int32_t* is_set);
+int tc_calibrate(ovn_handle* h, const float* d_volume, cudaStream_t s);
 // bounds-checked copies of index lists (d_idx_san): out-of-range entries are clamped and flagged in d_err
 int sanitize_indices(ovn_handle* h, const int32_t* d_in, int n, int64_t limit, int code, int32_t* d_out, cudaStream_t s);
 // read (and clear) the device error flag after the caller has synchronised `s`; maps it to a status

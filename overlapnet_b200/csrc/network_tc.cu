@@ -93,15 +93,17 @@ struct TcState {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_gather_rows_f16(const float* __restrict__ bank, const int32_t* __restrict__ idx, int n, const float* __restrict__ mu,
-                  __half* __restrict__ out) {
+                  int row_shift, __half* __restrict__ out) {
   const int64_t per = (int64_t)WF * CF / 4;            // float4 per volume
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)n * per) return;
   const int p = (int)(i / per);
   const int64_t e = i % per;
   const int64_t row = idx ? idx[p] : p;
-  const float4 v = __ldg(reinterpret_cast<const float4*>(bank + row * WF * CF) + e);
   const int64_t r = e / (CF / 4), c4 = e % (CF / 4);           // padded row pitch (K4_PITCH halves)
+  int64_t rs = r + row_shift;                                   // circular row shift (calibration pair only)
+  if (rs >= WF) rs -= WF;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(bank + (row * WF + rs) * CF) + c4);
   const float4 m = __ldg(reinterpret_cast<const float4*>(mu) + c4);
   __half2 a = __floats2half2_rn(v.x - m.x, v.y - m.y), b = __floats2half2_rn(v.z - m.z, v.w - m.w);
   uint2 o;
@@ -1995,7 +1997,7 @@ int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cuda
   return OVN_OK;
 }
 
-static int calibrate_center(ovn_handle* h, const float* d_vols, const int32_t* d_idx, int n, cudaStream_t s);
+static int calibrate_all(ovn_handle* h, const float* d_vols, const int32_t* d_idx, bool keep_mu, cudaStream_t s);
 
 int tc_bank_release(ovn_handle* h, const float* d_bank) {
   TcState* t = h->tc;
@@ -2026,11 +2028,11 @@ int tc_bank_prepare(ovn_handle* h, const float* d_bank, int64_t capacity, int64_
                                       (long long)t->pb_rows, (long long)first);
   const int64_t per = (int64_t)WF * CF / 4, perL = 3 * 2 * 8 * 128;
   const float* src = d_bank + (size_t)first * WF * CF;
-  if (!t->mu_set) {                     // first bank rows seen: calibrate the feature centre on (at most 16 of) them
-    int rc = calibrate_center(h, src, nullptr, count < 16 ? (int)count : 16, s);
+  if (!t->mu_set) {                     // first bank row seen by this handle: calibrate the centres on it
+    int rc = calibrate_all(h, src, nullptr, false, s);
     if (rc != OVN_OK) return rc;
   }
-  k_gather_rows_f16<<<(unsigned)((count * per + 255) / 256), 256, 0, s>>>(src, nullptr, (int)count, t->mu,
+  k_gather_rows_f16<<<(unsigned)((count * per + 255) / 256), 256, 0, s>>>(src, nullptr, (int)count, t->mu, 0,
                                                                          t->pb_l16 + (size_t)first * WF * K4_PITCH);
   OVN_LAUNCH_CHECK(h);
   k_pack_corr_L<<<(unsigned)((count * perL + 255) / 256), 256, 0, s>>>(src, nullptr, (int)count,
@@ -2040,13 +2042,57 @@ int tc_bank_prepare(ovn_handle* h, const float* d_bank, int64_t capacity, int64_
   return OVN_OK;
 }
 
-// ---- feature centre ------------------------------------------------------------------------------
-static int calibrate_center(ovn_handle* h, const float* d_vols, const int32_t* d_idx, int n, cudaStream_t s) {
+// ---- calibration of the three centres ----------------------------------------------------------------
+// Everything is derived from ONE volume V0 (the first one the handle sees: first bank row prepared, else the
+// first RIGHT volume scored, or the one given to ovn_calibrate): mu = channel means of V0; the o1 / x3
+// centres are the channel means over the canonical pair (LEFT = V0, RIGHT = V0 rolled by half a turn) --
+// c_conv1 with centre 0 -> mean of o1 -> fold into b2eff; c_conv1 again (centred) + c_conv2 with centre 0
+// -> mean of x3 -> fold into b3eff.  All on the stream, fixed summation orders: two handles calibrated on
+// the same volume (e.g. every rank of a sharded bank) give bit-identical results.
+static int calibrate_all(ovn_handle* h, const float* d_vols, const int32_t* d_idx, bool keep_mu, cudaStream_t s) {
   TcState* t = h->tc;
-  k_channel_mean<<<1, 1024, 0, s>>>(d_vols, d_idx, n, t->mu);
+  const int base = kMaxLegLayers;
+  const int64_t per = (int64_t)WF * CF / 4;
+  if (!keep_mu) {
+    k_channel_mean<<<1, 1024, 0, s>>>(d_vols, d_idx, 1, t->mu);
+    OVN_LAUNCH_CHECK(h);
+  }
+  OVN_CUDA(h, cudaMemsetAsync(t->mu_o1, 0, 64 * sizeof(float), s));
+  OVN_CUDA(h, cudaMemsetAsync(t->mu_x3, 0, 128 * sizeof(float), s));
+  k_gather_rows_f16<<<(unsigned)((per + 255) / 256), 256, 0, s>>>(d_vols, d_idx, 1, t->mu, 0, t->l16);
+  OVN_LAUNCH_CHECK(h);
+  k_gather_rows_f16<<<(unsigned)((per + 255) / 256), 256, 0, s>>>(d_vols, d_idx, 1, t->mu, WF / 2, t->r16);
+  OVN_LAUNCH_CHECK(h);
+  const int64_t Mc = PAIR_ROWS;
+  const int n_it_c = (int)((Mc + 255) / 256);
+  const int g4c = NB < h->sm_count ? NB : h->sm_count;
+  k_delta_conv1_tc<<<g4c, K4_THREADS, sizeof(K4Smem), s>>>(t->l16, nullptr, t->r16, 0, t->w1p, t->mu_o1, t->o1, 1, h->d_err);
+  OVN_LAUNCH_CHECK(h);
+  k_o1_channel_mean<<<1, 1024, 0, s>>>(t->o1, Mc, t->mu_o1);
+  OVN_LAUNCH_CHECK(h);
+  k_fold_bias2<<<1, 128, 0, s>>>(t->b2base, t->mu_o1, h->d_w[base + 1], t->b2eff);
+  OVN_LAUNCH_CHECK(h);
+  k_delta_conv1_tc<<<g4c, K4_THREADS, sizeof(K4Smem), s>>>(t->l16, nullptr, t->r16, 0, t->w1p, t->mu_o1, t->o1, 1, h->d_err);
+  OVN_LAUNCH_CHECK(h);
+  k_conv2_sw_tc<<<n_it_c, G_THREADS, sizeof(C2Smem), s>>>(t->o1, t->w2p, t->b2eff, t->mu_x3, t->x3, t->rows_pad, Mc, n_it_c, 0,
+                                                       h->d_err);
+  OVN_LAUNCH_CHECK(h);
+  k_x3_channel_mean<<<1, 1024, 0, s>>>(t->x3, t->rows_pad, Mc, t->mu_x3);
+  OVN_LAUNCH_CHECK(h);
+  k_fold_bias3<<<1, 256, 0, s>>>(h->d_b[base + 2], t->mu_x3, h->d_w[base + 2], t->b3eff);
   OVN_LAUNCH_CHECK(h);
   t->mu_set = true;
+  t->act_set = true;
   return OVN_OK;
+}
+
+int tc_calibrate(ovn_handle* h, const float* d_volume, cudaStream_t s) {
+  TcState* t = h->tc;
+  if (!t) OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "tensor-core weights not packed");
+  if (t->pb_key != nullptr)
+    OVN_SET_ERR(h, OVN_ERR_INVALID_ARG, "ovn_calibrate: release the resident bank first (its operand copies were built "
+                "with the previous centre)");
+  return calibrate_all(h, d_volume, nullptr, false, s);
 }
 
 int tc_set_center(ovn_handle* h, const float* h_mu) {
@@ -2088,12 +2134,12 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query, c
   const int maxp = h->cfg.max_batch_pairs;
   const int base = kMaxLegLayers;
   const int64_t per = (int64_t)WF * CF / 4;
-  if (!t->mu_set && n > 0) {            // first pairs seen by this handle: calibrate the feature centre on the RIGHT volume
-    int rc = d_query ? calibrate_center(h, d_query, nullptr, 1, s) : calibrate_center(h, d_bank, d_right, 1, s);
+  if ((!t->mu_set || !t->act_set) && n > 0) {     // first pairs seen by this handle: calibrate on the first RIGHT volume
+    int rc = d_query ? calibrate_all(h, d_query, nullptr, t->mu_set, s) : calibrate_all(h, d_bank, d_right, t->mu_set, s);
     if (rc != OVN_OK) return rc;
   }
   if (d_query) {
-    k_gather_rows_f16<<<(unsigned)((per + 255) / 256), 256, 0, s>>>(d_query, nullptr, 1, t->mu, t->r16);
+    k_gather_rows_f16<<<(unsigned)((per + 255) / 256), 256, 0, s>>>(d_query, nullptr, 1, t->mu, 0, t->r16);
     OVN_LAUNCH_CHECK(h);
   }
   const bool inject_fault = getenv("OVN_DEBUG_FAULT") != nullptr;            // tests/test_gpu_errors.py
@@ -2112,11 +2158,11 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query, c
       if (rc != OVN_OK) return rc;
       lidx = left = h->d_idx_san + 2 * (size_t)maxp;
     } else {
-      k_gather_rows_f16<<<(unsigned)((np * per + 255) / 256), 256, 0, s>>>(d_bank, left, np, t->mu, t->l16);
+      k_gather_rows_f16<<<(unsigned)((np * per + 255) / 256), 256, 0, s>>>(d_bank, left, np, t->mu, 0, t->l16);
       OVN_LAUNCH_CHECK(h);
     }
     if (!d_query) {
-      k_gather_rows_f16<<<(unsigned)((np * per + 255) / 256), 256, 0, s>>>(d_bank, right, np, t->mu, t->r16);
+      k_gather_rows_f16<<<(unsigned)((np * per + 255) / 256), 256, 0, s>>>(d_bank, right, np, t->mu, 0, t->r16);
       OVN_LAUNCH_CHECK(h);
     }
     const int64_t units = (int64_t)np * NB;
@@ -2124,32 +2170,6 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query, c
     const int64_t M = (int64_t)np * PAIR_ROWS;
     const int n_iter2 = (int)((M + 255) / 256);
     const int grid2 = n_iter2 < h->sm_count ? n_iter2 : h->sm_count;
-    if (!t->act_set) {
-      // One-time calibration of the o1 / x3 centres on (at most 8 of) the first pairs this handle scores:
-      // c_conv1 with centre 0 -> channel means of o1 -> fold into b2eff; c_conv1 again (centred) + c_conv2
-      // with centre 0 -> channel means of x3 -> fold into b3eff.  Everything on the stream, no host sync.
-      const int nc = np < 8 ? np : 8;
-      const int64_t Mc = (int64_t)nc * PAIR_ROWS;
-      const int n_it_c = (int)((Mc + 255) / 256);
-      const int64_t uc = (int64_t)nc * NB;
-      const int g4c = uc < h->sm_count ? (int)uc : h->sm_count;
-      k_delta_conv1_tc<<<g4c, K4_THREADS, sizeof(K4Smem), s>>>(l16, lidx, t->r16, d_query ? 0 : 1, t->w1p, t->mu_o1, t->o1, nc, h->d_err);
-      OVN_LAUNCH_CHECK(h);
-      k_o1_channel_mean<<<1, 1024, 0, s>>>(t->o1, Mc, t->mu_o1);
-      OVN_LAUNCH_CHECK(h);
-      k_fold_bias2<<<1, 128, 0, s>>>(t->b2base, t->mu_o1, h->d_w[base + 1], t->b2eff);
-      OVN_LAUNCH_CHECK(h);
-      k_delta_conv1_tc<<<g4c, K4_THREADS, sizeof(K4Smem), s>>>(l16, lidx, t->r16, d_query ? 0 : 1, t->w1p, t->mu_o1, t->o1, nc, h->d_err);
-      OVN_LAUNCH_CHECK(h);
-      k_conv2_sw_tc<<<n_it_c < h->sm_count ? n_it_c : h->sm_count, G_THREADS, sizeof(C2Smem), s>>>(
-          t->o1, t->w2p, t->b2eff, t->mu_x3, t->x3, t->rows_pad, Mc, n_it_c, 0, h->d_err);
-      OVN_LAUNCH_CHECK(h);
-      k_x3_channel_mean<<<1, 1024, 0, s>>>(t->x3, t->rows_pad, Mc, t->mu_x3);
-      OVN_LAUNCH_CHECK(h);
-      k_fold_bias3<<<1, 256, 0, s>>>(h->d_b[base + 2], t->mu_x3, h->d_w[base + 2], t->b3eff);
-      OVN_LAUNCH_CHECK(h);
-      t->act_set = true;
-    }
     prof_mark(h, PROF_DELTA, s);
     k_delta_conv1_tc<<<grid4, K4_THREADS, sizeof(K4Smem), s>>>(l16, lidx, t->r16, d_query ? 0 : 1, t->w1p, t->mu_o1, t->o1, np, h->d_err);
     prof_mark(h, PROF_DELTA, s);

@@ -104,6 +104,11 @@ class Engine:
       ptr = mu.ctypes.data_as(C.c_void_p)
     check(self._h, lib().ovn_set_feature_center(self._h, ptr), 'ovn_set_feature_center')
 
+  def calibrate(self, volume):
+    """ovn_calibrate: derive the three centres of the tensor-core heads from this [360,128] volume."""
+    v = volume.to(device=self.device, dtype=torch.float32).contiguous()
+    check(self._h, lib().ovn_calibrate(self._h, _ptr(v), self._stream()), 'ovn_calibrate')
+
   def get_feature_center(self):
     mu = np.zeros(FEAT_C, np.float32)
     is_set = C.c_int32(0)

@@ -218,7 +218,8 @@ class ShardedBank:
   def owner(self, frame_id):
     return int(frame_id) % self.world
 
-  def step(self, frame_id, reference_ids):
+  def step(self, frame_id, reference_ids, on_query=None):
+    """``on_query(frame_id, volume)`` is called on every rank once the current frame's volume is there."""
     if int(frame_id) != self.n_frames:
       raise Exception('frames must arrive in order 0,1,2,... (got %d, expected %d)' % (frame_id, self.n_frames))
     if self.rank == self.src:
@@ -227,6 +228,8 @@ class ShardedBank:
       q = torch.empty(self.fv_shape, dtype=torch.float32, device=self.device)
     if self.world > 1:
       dist.broadcast(q, self.src, group=self.group)
+    if on_query is not None:
+      on_query(int(frame_id), q)
     if self.owner(frame_id) == self.rank:
       self.append_fn(q)
     self.n_frames += 1

@@ -38,13 +38,19 @@ class ShardedInfer(Infer):
 
   def infer_multiple(self, current_frame_id, reference_frame_id):
     """infer.py:162-203 on the sharded bank.  LEFT = reference frames, RIGHT = the current frame."""
-    res = self._sb.step(current_frame_id, reference_frame_id)
+    res = self._sb.step(current_frame_id, reference_frame_id, on_query=self._on_query)
     self._engine.check()
     if res is None:
       return None
     ov, yaw = res
     overlap = ov.cpu().numpy()[:, None]
     return overlap.squeeze(), yaw.cpu().numpy().astype(np.int64)
+
+  def _on_query(self, frame_id, q):
+    # every rank derives the numeric centres of the tensor-core heads from frame 0 (ovn_calibrate), like a
+    # single-GPU Infer does implicitly with its first bank row: sharded and unsharded results are bit-identical
+    if frame_id == 0:
+      self._engine.calibrate(q)
 
   @property
   def local_frames(self):
