@@ -341,7 +341,13 @@ def main():
 
   extras = {}
   if not args.no_extras:
-    extras = measure_extras(args, eng, w, dev, rank, world, local, timed, q_dev, q_host, cloud_batch, fv_src, bank)
+    leg_ms = prof['leg'][0] / max(args.steps, 1)
+    per_pair_ms = max(ms / max(args.steps, 1) - leg_ms, 1e-6) / N_CAND
+    disc = torch.tensor([int(round(leg_ms / per_pair_ms))], dtype=torch.int32, device=dev)
+    if world > 1:
+      dist.broadcast(disc, 0)
+    extras = measure_extras(args, eng, w, dev, rank, world, local, timed, q_dev, q_host, cloud_batch, fv_src, bank,
+                            int(disc.item()))
 
   if rank == 0:
     pk = peaks()
@@ -410,12 +416,12 @@ def main():
     dist.destroy_process_group()
 
 
-def measure_extras(args, eng, w, dev, rank, world, local, timed, q_dev, q_host, cloud_batch, fv_src, bank):
+def measure_extras(args, eng, w, dev, rank, world, local, timed, q_dev, q_host, cloud_batch, fv_src, bank, src_discount):
   """The other BASELINE configs, each a short measurement in the same run (see the module docstring)."""
   import torch.distributed as dist
   from overlapnet_b200 import synth
   from overlapnet_b200.engine import CloudBatch, Engine
-  from overlapnet_b200.search import ShardedSearch, engine_heads_fn, shard_range
+  from overlapnet_b200.search import ShardedSearch, balanced_sizes, engine_heads_fn, shard_range
   out = {}
   pk = peaks()
   n_q = len(q_dev)
@@ -524,12 +530,15 @@ def measure_extras(args, eng, w, dev, rank, world, local, timed, q_dev, q_host, 
       out['leg_batch256'] = {'error': repr(e)[:300]}
 
   # ---- config 4: 4541-volume bank SHARDED over the ranks (strong scaling) -----------------------------
-  lo, hi = shard_range(N_BANK4, rank, world)
+  # rank 0 also encodes the query: its shard is shorter by (encode time / time per candidate) candidates
+  sizes4 = balanced_sizes(N_BANK4, world, 0, src_discount)
+  lo = int(sum(sizes4[:rank]))
+  hi = lo + sizes4[rank]
   eng.bank_release(None)
   big = rolled_bank(eng, fv_src, N_BANK4, dev)[lo:hi].contiguous()
   eng.bank_prepare(big)
   qfv = torch.empty((eng.Wf, 128), dtype=torch.float32, device=dev)
-  ss4 = ShardedSearch(engine_heads_fn(eng), big, N_BANK4, transport=args.transport) if world > 1 else None
+  ss4 = ShardedSearch(engine_heads_fn(eng), big, N_BANK4, transport=args.transport, sizes=sizes4) if world > 1 else None
 
   def step4(i):
     if rank == 0:
@@ -542,8 +551,8 @@ def measure_extras(args, eng, w, dev, rank, world, local, timed, q_dev, q_host, 
   ms4 = timed(step4, k4, 2)
   eng.check()
   if rank == 0:
-    out['bank4541'] = {'workload': 'BASELINE config 4: 1 query x 4541-volume bank sharded over %d GPU(s) (%d per GPU)'
-                                   % (world, hi - lo),
+    out['bank4541'] = {'workload': 'BASELINE config 4: 1 query x 4541-volume bank sharded over %d GPU(s), shard sizes %s '
+                                   '(rank 0 also encodes the query)' % (world, sizes4),
                        'scaling': 'strong', 'pairs_per_s': N_BANK4 * k4 / (ms4 * 1e-3), 'ms_per_query': ms4 / k4,
                        'steps': k4, 'transport': ss4.transport if ss4 else 'single GPU'}
 
@@ -573,6 +582,7 @@ def measure_extras(args, eng, w, dev, rank, world, local, timed, q_dev, q_host, 
   ms_rows = timed(rows_step, 3, 1) / 3
   eng.check()
   t_ag = None
+  lo, hi = shard_range(N_BANK4, rank, world)
   if world > 1:
     shard = full[lo:hi].contiguous()
     pad = torch.zeros((shard_range(N_BANK4, 0, world)[1],) + tuple(shard.shape[1:]), dtype=shard.dtype, device=dev)

@@ -204,6 +204,17 @@ int ovn_bank_release(ovn_handle* h, const float* d_bank);
  * cleared when it is reported. */
 int ovn_check(ovn_handle* h, void* stream);
 
+/* ---- device-side signalling between the GPUs of a sharded bank (overlapnet_b200/search.py, transport 'symm') --
+ * The query volume and the result table of a sharded 1-vs-N search live in symmetric (peer-mapped) memory:
+ * kernels read / write them directly over NVLink, and these two calls replace the collectives.  A flag is an
+ * int32 slot in that memory holding the number of the last finished step.
+ *   ovn_peer_signal: ONE launch stores `value` (release, system scope -- after everything queued on `stream`
+ *                    before it) to each of the n flag addresses (host array of peer-mapped device addresses).
+ *   ovn_peer_wait:   ONE launch spins (acquire, system scope, bounded) until d_flags[i] >= value for every
+ *                    i < n except i == skip.  A time-out raises the handle's deferred error (ovn_check). */
+int ovn_peer_signal(ovn_handle* h, const uint64_t* h_flag_ptrs, int32_t n, int32_t value, void* stream);
+int ovn_peer_wait(ovn_handle* h, const int32_t* d_flags, int32_t n, int32_t skip, int32_t value, void* stream);
+
 /* ---- feature centre of the tensor-core delta head ------------------------------------------------
  * DeltaLayer only sees |l - r| (generateNet.py:59), which is invariant to a common per-channel offset:
  * the fp16 operand copies of the volumes are stored as fp16(x - mu[c]), which shrinks their rounding

@@ -19,7 +19,7 @@ SYMBOLS = [
     'ovn_pack_input',
     'ovn_leg_forward', 'ovn_heads_forward', 'ovn_heads_1vsN', 'ovn_bank_prepare', 'ovn_bank_release', 'ovn_encode_clouds_host',
     'ovn_query_cloud_vs_bank_host', 'ovn_check', 'ovn_set_feature_center', 'ovn_get_feature_center',
-    'ovn_heads_rows_vs_bank', 'ovn_calibrate',
+    'ovn_heads_rows_vs_bank', 'ovn_calibrate', 'ovn_peer_signal', 'ovn_peer_wait',
 ]
 
 
@@ -90,6 +90,8 @@ def lib():
   L.ovn_set_feature_center.argtypes = [vp, vp]
   L.ovn_get_feature_center.argtypes = [vp, vp, C.POINTER(i32)]
   L.ovn_calibrate.argtypes = [vp, vp, vp]
+  L.ovn_peer_signal.argtypes = [vp, vp, i32, i32, vp]
+  L.ovn_peer_wait.argtypes = [vp, vp, i32, i32, i32, vp]
   L.ovn_encode_clouds_host.argtypes = [vp, vp, vp, i32, vp]
   L.ovn_query_cloud_vs_bank_host.argtypes = [vp, vp, i64, vp, i64, vp, i32, vp, vp, vp]
   _lib = L

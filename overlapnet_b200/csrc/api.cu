@@ -37,6 +37,32 @@ static __global__ void k_sanitize_idx(const int32_t* __restrict__ in, int32_t* _
   out[i] = (int32_t)v;
 }
 
+// ---- device-side signalling between the ranks of a sharded bank (search.py transport 'symm') ----------
+// Flags are int32 slots in symmetric (peer-mapped) memory holding the number of the last finished step.
+// One launch signals every peer (release at system scope, after everything this stream did before),
+// one launch waits for every peer (acquire at system scope, bounded).
+struct PeerPtrs { int32_t* p[16]; };
+
+static __global__ void k_peer_signal(PeerPtrs dst, int n, int value) {
+  const int i = threadIdx.x;
+  if (i >= n || dst.p[i] == nullptr) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(dst.p[i]), "r"(value) : "memory");
+}
+
+static __global__ void k_peer_wait(const int32_t* __restrict__ flags, int n, int skip, int value, int* __restrict__ err) {
+  const int i = threadIdx.x;
+  if (i >= n || i == skip) return;
+  const long long t0 = clock64();
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+    if (v >= value) break;
+    if (clock64() - t0 > (1ll << 32)) { atomicCAS(err, 0, 950); break; }     // ~2 s: a peer died
+    __nanosleep(32);
+  }
+}
+
 namespace ovn {
 
 int sanitize_indices(ovn_handle* h, const int32_t* d_in, int n, int64_t limit, int code, int32_t* d_out, cudaStream_t s) {
@@ -59,6 +85,7 @@ int check_device_error(ovn_handle* h, cudaStream_t s) {
   if (e == kErrBadIndex) OVN_SET_ERR(h, OVN_ERR_INVALID_ARG, "a pair / candidate index is outside [0, bank_size)");
   if (e == kErrRowNotPrepared)
     OVN_SET_ERR(h, OVN_ERR_INVALID_ARG, "resident bank: an indexed row was never passed to ovn_bank_prepare");
+  if (e == 950) OVN_SET_ERR(h, OVN_ERR_CUDA, "ovn_peer_wait timed out: a peer rank never signalled");
   OVN_SET_ERR(h, OVN_ERR_CUDA, "tensor-core pipeline barrier timed out (code %d); outputs of the call are poisoned (NaN / INT32_MIN)", e);
 }
 
@@ -553,6 +580,28 @@ int ovn_bank_prepare(ovn_handle* h, const float* d_bank, int64_t bank_capacity, 
   int rc = tc_bank_prepare(h, d_bank, bank_capacity, first, count, (cudaStream_t)stream);
   if (rc == OVN_OK) OVN_CUDA(h, cudaEventRecord(h->ev_bank, (cudaStream_t)stream));
   return rc;
+}
+
+int ovn_peer_signal(ovn_handle* h, const uint64_t* h_flag_ptrs, int32_t n, int32_t value, void* stream) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
+  REQUIRE(h, h_flag_ptrs != nullptr && n >= 0 && n <= 16, "bad peer list (at most 16 peers)");
+  if (n == 0) return OVN_OK;
+  PeerPtrs pp = {};
+  for (int i = 0; i < n; ++i) pp.p[i] = reinterpret_cast<int32_t*>(h_flag_ptrs[i]);
+  k_peer_signal<<<1, 32, 0, (cudaStream_t)stream>>>(pp, n, value);
+  OVN_LAUNCH_CHECK(h);
+  return OVN_OK;
+}
+
+int ovn_peer_wait(ovn_handle* h, const int32_t* d_flags, int32_t n, int32_t skip, int32_t value, void* stream) {
+  if (!h) return OVN_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
+  REQUIRE(h, d_flags != nullptr && n >= 0 && n <= 32, "bad flag list");
+  if (n == 0) return OVN_OK;
+  k_peer_wait<<<1, 32, 0, (cudaStream_t)stream>>>(d_flags, n, skip, value, h->d_err);
+  OVN_LAUNCH_CHECK(h);
+  return OVN_OK;
 }
 
 int ovn_check(ovn_handle* h, void* stream) {

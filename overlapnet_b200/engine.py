@@ -104,6 +104,15 @@ class Engine:
       ptr = mu.ctypes.data_as(C.c_void_p)
     check(self._h, lib().ovn_set_feature_center(self._h, ptr), 'ovn_set_feature_center')
 
+  def peer_signal(self, flag_addrs, value):
+    """ovn_peer_signal: one launch stores ``value`` (release.sys) to each peer-mapped flag address."""
+    arr = (C.c_uint64 * len(flag_addrs))(*[int(a) for a in flag_addrs])
+    check(self._h, lib().ovn_peer_signal(self._h, arr, len(flag_addrs), int(value), self._stream()), 'ovn_peer_signal')
+
+  def peer_wait(self, flags, n, skip, value):
+    """ovn_peer_wait: one launch waits until flags[i] >= value for every i < n except ``skip``."""
+    check(self._h, lib().ovn_peer_wait(self._h, _ptr(flags), int(n), int(skip), int(value), self._stream()), 'ovn_peer_wait')
+
   def calibrate(self, volume):
     """ovn_calibrate: derive the three centres of the tensor-core heads from this [360,128] volume."""
     v = volume.to(device=self.device, dtype=torch.float32).contiguous()

@@ -41,8 +41,23 @@ def unpack_records(rec):
   return rec[:, 0].contiguous().view(torch.float32), rec[:, 1].contiguous()
 
 
+def balanced_sizes(n, world, src, src_discount):
+  """Shard sizes when rank ``src`` also encodes the query: it gets ``src_discount`` fewer candidates
+  (= encode time / time per candidate), the rest is spread evenly.  Returns a list of ``world`` sizes."""
+  d = int(max(0, min(src_discount, n // max(world, 1))))
+  if world == 1:
+    return [n]
+  base, rem = divmod(n + d, world)
+  sizes = [base + (1 if r < rem else 0) for r in range(world)]
+  sizes[src] -= d
+  if sizes[src] < 0:
+    return [hi - lo for lo, hi in (shard_range(n, r, world) for r in range(world))]
+  assert sum(sizes) == n
+  return sizes
+
+
 class _SymmTransport:
-  """Peer-mapped query buffer + result table (torch.distributed._symmetric_memory)."""
+  """Peer-mapped query buffer + result table + step flags (torch.distributed._symmetric_memory)."""
 
   def __init__(self, n_slots, fv_shape, device, group):
     import torch.distributed._symmetric_memory as symm_mem
@@ -52,12 +67,19 @@ class _SymmTransport:
     self.n_slots = int(n_slots)
     qn = int(np.prod(self.fv_shape))
     self.q_words = qn
-    # one allocation: [query fp32 | overlap fp32 x world x n_slots | yaw i32 x world x n_slots]
-    total = qn + 2 * self.world * self.n_slots
+    # one allocation: [query fp32 | overlap fp32 x world x n_slots | yaw i32 x world x n_slots | flags i32 x 2 x world]
+    self.flag_off = qn + 2 * self.world * self.n_slots
+    total = self.flag_off + 2 * self.world
     self.buf = symm_mem.empty(total, dtype=torch.float32, device=device)
     self.hdl = symm_mem.rendezvous(self.buf, self.group)
     self.buf.zero_()
     self.hdl.barrier(channel=2)
+    self.step = 0
+    # flags[c][r] on rank d = "rank r finished step <value> of channel c" (c 0: query in place, c 1: results stored)
+    self.my_flags = [self.hdl.get_buffer(self.rank, (self.world,), torch.int32, self.flag_off + c * self.world)
+                     for c in range(2)]
+    self.peer_flag_addr = [[self.hdl.get_buffer(d, (1,), torch.int32, self.flag_off + c * self.world + self.rank).data_ptr()
+                            for d in range(self.world)] for c in range(2)]
 
   def query_view(self, rank):
     return self.hdl.get_buffer(rank, self.fv_shape, torch.float32, 0)
@@ -75,29 +97,43 @@ class ShardedSearch:
   the same device as its inputs.  ``bank_local`` is this rank's contiguous block of the bank.
   With ``transport='symm'`` the function must also accept ``out=(overlap, yaw)`` tensors to write into."""
 
-  def __init__(self, heads_1vsN_fn, bank_local, n_total, group=None, transport='collective'):
+  def __init__(self, heads_1vsN_fn, bank_local, n_total, group=None, transport='collective', sizes=None):
     self.fn = heads_1vsN_fn
     self.bank = bank_local
     self.n_total = int(n_total)
     self.group = group
     self.rank = dist.get_rank(group) if dist.is_initialized() else 0
     self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-    self.lo, self.hi = shard_range(self.n_total, self.rank, self.world)
+    if sizes is None:                      # contiguous blocks, equal up to one (``sizes``: explicit, e.g. balanced_sizes)
+      self.sizes = [shard_range(self.n_total, r, self.world) for r in range(self.world)]
+    else:
+      offs = np.concatenate([[0], np.cumsum(sizes)])
+      assert len(sizes) == self.world and int(offs[-1]) == self.n_total
+      self.sizes = [(int(offs[r]), int(offs[r + 1])) for r in range(self.world)]
+    self.lo, self.hi = self.sizes[self.rank]
     if bank_local.shape[0] != self.hi - self.lo:
       raise Exception('rank %d holds %d volumes, its shard is [%d, %d)' % (self.rank, bank_local.shape[0],
                                                                           self.lo, self.hi))
-    self.sizes = [shard_range(self.n_total, r, self.world) for r in range(self.world)]
     self.max_shard = max(hi - lo for lo, hi in self.sizes)
+    # own signalling kernels (ovn_peer_signal / ovn_peer_wait: one launch each) when the compute is the engine
+    self.engine = getattr(heads_1vsN_fn, 'engine', None)
     self.transport = 'collective'
     self.symm = None
     if transport in ('symm', 'auto') and self.world > 1 and bank_local.is_cuda:
+      ok = 1
       try:
         self.symm = _SymmTransport(self.max_shard, bank_local.shape[1:], bank_local.device, group)
-        self.transport = 'symm'
       except Exception as e:                      # no peer access / old torch: fall back to the collectives
-        if transport == 'symm':
-          raise
+        ok = 0
         self.symm_error = repr(e)
+      flag = torch.tensor([ok], dtype=torch.int32, device=bank_local.device)
+      dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)       # every rank must take the same path
+      if int(flag.item()) == 1:
+        self.transport = 'symm'
+      else:
+        self.symm = None
+        if transport == 'symm':
+          raise Exception('symmetric-memory transport unavailable: %s' % getattr(self, 'symm_error', 'on another rank'))
     if self.world > 1 and self.transport == 'collective':
       dev = bank_local.device
       self._pad = torch.zeros((self.max_shard, 2), dtype=torch.int32, device=dev)
@@ -127,22 +163,35 @@ class ShardedSearch:
   def _query_symm(self, query_fv, src):
     s = self.symm
     m = self.hi - self.lo
+    s.step += 1
+    eng = self.engine
     if self.rank == src:
       s.query_view(src).copy_(query_fv)                            # local store into the symmetric buffer
-      for r in range(self.world):
-        if r != src:
-          s.hdl.put_signal(r, channel=0)                           # "query k is in place"
+      if eng is not None:                                          # "query k is in place": ONE launch for all peers
+        eng.peer_signal([a for d, a in enumerate(s.peer_flag_addr[0]) if d != src], s.step)
+      else:
+        for r in range(self.world):
+          if r != src:
+            s.hdl.put_signal(r, channel=0)
+    elif eng is not None:
+      eng.peer_wait(s.my_flags[0][src:src + 1], 1, -1, s.step)
     else:
       s.hdl.wait_signal(src, channel=0)
     q = s.query_view(src)                                          # peers read it over NVLink inside their kernels
     ov_out, yaw_out = s.result_views(src, self.rank)               # rows of the SOURCE rank's table
     self.fn(self.bank, q, out=(ov_out[:m], yaw_out[:m]))
     if self.rank != src:
-      s.hdl.put_signal(src, channel=1)                             # "my results are in your table"
+      if eng is not None:                                          # "my results are in your table"
+        eng.peer_signal([s.peer_flag_addr[1][src]], s.step)
+      else:
+        s.hdl.put_signal(src, channel=1)
       return None
-    for r in range(self.world):
-      if r != src:
-        s.hdl.wait_signal(r, channel=1)
+    if eng is not None:
+      eng.peer_wait(s.my_flags[1], self.world, src, s.step)       # ONE launch waits for every peer
+    else:
+      for r in range(self.world):
+        if r != src:
+          s.hdl.wait_signal(r, channel=1)
     ov_all, yaw_all = [], []
     for r, (lo, hi) in enumerate(self.sizes):
       o, y = s.result_views(src, r)
@@ -267,6 +316,7 @@ def engine_heads_fn(engine):
   def fn(bank, query, out=None):
     ov, yaw, _ = engine.heads_1vsN(bank, query, n_cand=int(bank.shape[0]), out=out)
     return ov, yaw
+  fn.engine = engine
   return fn
 
 
