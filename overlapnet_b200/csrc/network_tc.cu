@@ -4,8 +4,8 @@
 //           c_conv2 (+ReLU) (generateNet.py:102-105)                -> k_conv2_sw_tc
 //           c_conv3 (+ReLU), Flatten + Dense(1, sigmoid) (:107-114) -> k_conv3_resident_tc + k_dense_finalize
 //           NormalizedCorrelation2D + argmax (:117-143, infer.py)   -> k_corr_tc + k_corr_finalize
-//           leg Conv2D stack (generateNet.py:149-230)               -> k_leg_layer1_direct, k_leg_resident_tc,
-//                                                                      k_gemm_stream_tc (batched)
+//           leg Conv2D stack (generateNet.py:149-230)               -> k_leg_layer1_direct, k_leg_resident_tc (1-2 scans),
+//                                                                      k_leg_batched_tc (batched)
 //
 // k_delta_conv1_tc (the kernel that decides scan-pairs/s; 83 % of the FLOPs of a pair)
 //   GEMM view per pair:  o1[(i, jb), o] = sum_{dj<15, c<128} |L[i,c] - R[15 jb + dj, c]| W1[dj, c, o]
@@ -49,12 +49,7 @@ struct TcState {
   __half* w3p = nullptr;        // [2 halves][36 slabs][4][128][8]
   float* b2eff = nullptr;       // c_conv2 bias + the c_conv1 bias pushed through W2 (both layers are linear)
   // tensor-core leg (layers 2..): packed weights + copy tables per layer, ping-pong activation planes
-  __half* wleg[kMaxLegLayers] = {};      // [1][n_slabs][4][NT][8]   (throughput mode)
-  __half* wres[kMaxLegLayers] = {};      // [cout/64][kh*kw*3][C_in/8][64][8] (latency mode, resident activations)
-  int* leg_plane[kMaxLegLayers] = {};
-  int* leg_shift[kMaxLegLayers] = {};
-  int leg_slabs[kMaxLegLayers] = {};
-  int leg_nt[kMaxLegLayers] = {};
+  __half* wres[kMaxLegLayers] = {};      // [cout/64][kh*kw*3][C_in/8][64][8] (resident-activation kernels)
   __half* actp[2] = {nullptr, nullptr};
   float* leg_part = nullptr;     // split-K partial tiles of the latency-mode leg: [kLegPartTiles][128 x 64] fp32
   int* leg_counters = nullptr;   // [kLegPartTiles * 4] arrival counters (always left at zero)
@@ -514,193 +509,7 @@ done:
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_gemm_stream_tc -- the batched leg (many scans per launch): one CTA per output image row,
-// D[512 rows x NT] += sum over K slabs of A_slab[512 x 32] * B_slab[NT x 32]^T with both operands
-// streamed global -> shared by cp.async.bulk in the C8-interleaved layout; a per-copy row shift is
-// the convolution tap along the row (implicit im2col at the copy level).  The single-scan leg uses
-// k_leg_resident_tc instead (activation window resident, split-K, programmatic dependent launch).
-// ------------------------------------------------------------------------------------------------
 constexpr int G_THREADS = 256;
-
-// TILES = 128-row tiles per CTA: 4 (W slabs are reused by four tiles, 4-deep ring of 40 KB stages)
-template <int NT, int TILES>
-struct GCfg {
-  static constexpr int ROWS = TILES * 128;
-  static constexpr int A_BYTES = 4 * ROWS * 16;       // 4 planes x ROWS x 16 B
-  static constexpr int B_BYTES = 4 * NT * 16;         // 4 planes x NT x 16 B
-  static constexpr int STAGES = TILES == 4 ? 4 : 12;
-};
-
-template <int NT, int TILES>
-struct GSmem {
-  using C = GCfg<NT, TILES>;
-  uint8_t A[C::STAGES][C::A_BYTES];
-  uint8_t B[C::STAGES][C::B_BYTES];
-  float bias[128];
-  int2 tab[1024];               // (plane, shift) of every copy, staged once: the loader thread must not chase global loads
-  uint64_t full[C::STAGES], empty[C::STAGES], d_full;
-  uint32_t tmem_base;
-};
-
-// One "run" = a 1-D sequence of rows (pixels) whose channels live in C8-interleaved planes
-// [plane][row][8] with `a_pitch` rows per plane.  blockIdx.x = 512-row tile inside the run,
-// blockIdx.y = run (image row for the 2-D leg layers), blockIdx.z = 128-wide N slice.
-// K loop = slabs of four (plane, row shift) copies: the row shift is the convolution tap along
-// the run (implicit im2col at the copy level), the plane picks (input row tap, channel chunk).
-struct GemmArgs {
-  const __half* A;
-  int64_t a_pitch;            // rows per input plane
-  const int* copy_plane;      // [n_slabs*4] plane of each copy, relative to the run's first plane
-  const int* copy_shift;      // [n_slabs*4] row shift of each copy
-  int n_slabs;
-  const __half* Bp;           // [gridDim.z][n_slabs][4][NT][8]
-  const float* bias;          // [gridDim.z * NT]
-  int64_t M;                  // valid rows per run
-  int runs_per_img;           // blockIdx.y = img * runs_per_img + run
-  int in_img_planes;          // planes per input image
-  int in_run_planes;          // plane advance per run (stride_h * C8_in)
-  // epilogue 4: bias + ReLU -> hi/lo fp16 planes [y * out_run_planes + {hi, lo}][n/8][row][8]
-  __half* out_planes; int64_t out_pitch; int out_run_planes;
-  // epilogue 3: bias + ReLU -> fp32 row-major [y][row][NT]
-  float* out_f32;
-  int n_valid;                // output channels actually present (<= NT); 0 = NT
-};
-
-template <int EPI, int NT, int TILES>
-__global__ void __launch_bounds__(G_THREADS, 1)
-k_gemm_stream_tc(GemmArgs g, int* __restrict__ err) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  using C = GCfg<NT, TILES>;
-  GSmem<NT, TILES>& S = *reinterpret_cast<GSmem<NT, TILES>*>(smem_raw);
-  constexpr int B_BYTES = C::B_BYTES, G_ROWS = C::ROWS, G_A_BYTES = C::A_BYTES, G_STAGES = C::STAGES;
-  constexpr uint32_t TMEM_COLS = (TILES * NT) <= 64 ? 64 : ((TILES * NT) <= 128 ? 128 : ((TILES * NT) <= 256 ? 256 : 512));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t row0 = (int64_t)blockIdx.x * G_ROWS;
-  const int y = blockIdx.y, nh = blockIdx.z;
-  const int64_t in_base = (int64_t)(y / g.runs_per_img) * g.in_img_planes + (int64_t)(y % g.runs_per_img) * g.in_run_planes;
-
-  if (tid == 0) {
-    for (int s = 0; s < G_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-    mbar_init(&S.d_full, 1);
-    mbar_fence_init();
-  }
-  if (tid < NT) S.bias[tid] = (g.n_valid == 0 || nh * NT + tid < g.n_valid) ? g.bias[nh * NT + tid] : 0.f;
-  for (int e = tid; e < g.n_slabs * 4; e += G_THREADS) S.tab[e] = make_int2(g.copy_plane[e], g.copy_shift[e]);
-  if (warp == 2) tmem_alloc(&S.tmem_base, TMEM_COLS);
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem = S.tmem_base;
-
-  if (warp == 0) {
-    // the whole warp walks the ring; lanes 0..3 each issue one activation-plane copy and lane 4 the
-    // weight slab, so a slab costs one bulk-copy issue latency instead of five in a row
-    uint32_t s = 0, ph = 0;
-    for (int sl = 0; sl < g.n_slabs; ++sl) {
-      TC_WAIT(&S.empty[s], ph ^ 1, 501);
-      if (lane == 0) mbar_arrive_expect_tx(&S.full[s], G_A_BYTES + B_BYTES);
-      __syncwarp();
-      if (lane < 4) {
-        const int2 ps = S.tab[sl * 4 + lane];
-        const int64_t plane = in_base + ps.x;
-        const int64_t r = row0 + ps.y;
-        bulk_g2s(S.A[s] + lane * (G_ROWS * 16), g.A + ((size_t)plane * g.a_pitch + r) * 8, G_ROWS * 16, &S.full[s]);
-      } else if (lane == 4) {
-        bulk_g2s(S.B[s], g.Bp + ((size_t)nh * g.n_slabs + sl) * (B_BYTES / 2), B_BYTES, &S.full[s]);
-      }
-      if (++s == G_STAGES) { s = 0; ph ^= 1; }
-    }
-  } else if (warp == 1) {
-    // warp-uniform loop, one elected lane issues; descriptors advance by 32-bit adds
-    const uint32_t idesc = make_idesc_f16(128, NT);
-    const bool leader = elect_one() != 0;
-    const uint64_t ad0 = make_desc_kmajor_noswizzle(smem_u32(S.A[0]), G_ROWS * 16, 128);
-    const uint64_t bd0 = make_desc_kmajor_noswizzle(smem_u32(S.B[0]), NT * 16, 128);
-    const uint32_t ad_hi = (uint32_t)(ad0 >> 32), ad_lo = (uint32_t)ad0;
-    const uint32_t bd_hi = (uint32_t)(bd0 >> 32), bd_lo = (uint32_t)bd0;
-    uint32_t sg = 0, ph = 0;
-    for (int sl = 0; sl < g.n_slabs; ++sl) {
-      TC_WAIT(&S.full[sg], ph, 502);
-      fence_after_sync();
-      if (leader) {
-        const uint32_t a_off = (sg * G_A_BYTES) >> 4, b_off = (sg * B_BYTES) >> 4;
-#pragma unroll
-        for (int t = 0; t < TILES; ++t) {
-#pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const uint64_t ad = ((uint64_t)ad_hi << 32) | (uint64_t)(ad_lo + a_off + ((t * 128 * 16 + kk * 2 * (G_ROWS * 16)) >> 4));
-            const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(bd_lo + b_off + ((kk * 2 * (NT * 16)) >> 4));
-            mma_ss(tmem + t * NT, ad, bd, idesc, (sl | kk) != 0);
-          }
-        }
-        commit(&S.empty[sg]);
-      }
-      __syncwarp();
-      if (++sg == G_STAGES) { sg = 0; ph ^= 1; }
-    }
-    if (leader) commit(&S.d_full);
-    __syncwarp();
-  } else if (warp >= 4) {
-    const int q = warp & 3;
-    TC_WAIT(&S.d_full, 0, 503);
-    fence_after_sync();
-#pragma unroll 1
-    for (int t = 0; t < TILES; ++t) {
-      const int64_t r = row0 + t * 128 + q * 32 + lane;
-      {
-#pragma unroll 1
-        for (int c0 = 0; c0 < NT; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * NT + c0, v);
-          tmem_ld_wait();
-          if (r < g.M && (g.n_valid == 0 || nh * NT + c0 < g.n_valid)) {
-            if (EPI == 4) {
-              // bias + ReLU -> hi/lo fp16 split planes (x = hi + lo to 2^-22): the next layer's
-              // three-term product keeps the leg at fp32-grade accuracy on the fp16 tensor pipe
-#pragma unroll
-              for (int h8 = 0; h8 < 2; ++h8) {
-                uint32_t ph[4], pl[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int n = c0 + h8 * 8 + 2 * j;
-                  const float a = fmaxf(__uint_as_float(v[h8 * 8 + 2 * j]) + S.bias[n], 0.f);
-                  const float b = fmaxf(__uint_as_float(v[h8 * 8 + 2 * j + 1]) + S.bias[n + 1], 0.f);
-                  const __half2 hi = __floats2half2_rn(a, b);
-                  const float2 hf = __half22float2(hi);
-                  const __half2 lo = __floats2half2_rn(a - hf.x, b - hf.y);
-                  ph[j] = *reinterpret_cast<const uint32_t*>(&hi);
-                  pl[j] = *reinterpret_cast<const uint32_t*>(&lo);
-                }
-                const int c8 = nh * (NT / 8) + (c0 >> 3) + h8;
-                const int64_t plane = (int64_t)y * g.out_run_planes + c8;
-                *reinterpret_cast<uint4*>(g.out_planes + ((size_t)plane * g.out_pitch + r) * 8) =
-                    make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                *reinterpret_cast<uint4*>(g.out_planes + ((size_t)(plane + g.out_run_planes / 2) * g.out_pitch + r) * 8) =
-                    make_uint4(pl[0], pl[1], pl[2], pl[3]);
-              }
-            } else {
-              float* dst = g.out_f32 + ((size_t)y * g.M + r) * (g.n_valid ? g.n_valid : NT) + nh * NT + c0;
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                float4 o;
-                o.x = fmaxf(__uint_as_float(v[j4 * 4 + 0]) + S.bias[c0 + j4 * 4 + 0], 0.f);
-                o.y = fmaxf(__uint_as_float(v[j4 * 4 + 1]) + S.bias[c0 + j4 * 4 + 1], 0.f);
-                o.z = fmaxf(__uint_as_float(v[j4 * 4 + 2]) + S.bias[c0 + j4 * 4 + 2], 0.f);
-                o.w = fmaxf(__uint_as_float(v[j4 * 4 + 3]) + S.bias[c0 + j4 * 4 + 3], 0.f);
-                reinterpret_cast<float4*>(dst)[j4] = o;
-              }
-            }
-          }
-        }
-      }
-    }
-  }
-done:
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, TMEM_COLS);
-}
 
 // ------------------------------------------------------------------------------------------------
 // k_conv2_sw_tc -- c_conv2 (15x1 stride 15, 64 -> 128, ReLU) as a GEMM  [M x 960] x [960 x 128].
@@ -1242,6 +1051,174 @@ done:
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_leg_batched_tc -- one leg layer for a BATCH of scans (throughput mode).
+// The streamed GEMM (k_gemm_stream_tc) re-read the activation rows from L2 for every (dh, dw, term) tap:
+// 103 MB of L2 -> shared traffic per scan, 5.9 TB/s at 17.5 us/scan -- L2-bandwidth bound (profiles/
+// r2_leg_batched.txt).  Here, as in the latency-mode kernel, the activation window of the CTA's output
+// pixels is loaded ONCE and every tap is a descriptor offset; a CTA owns TILES consecutive 128-pixel
+// tiles so that each streamed weight slab is used TILES times (27 MB of L2 traffic per scan).
+// No split-K: a batch gives every layer enough tiles to fill the GPU.
+// ------------------------------------------------------------------------------------------------
+constexpr int LB_A_MAX = 139264;                  // 2 x 2 x 8 planes x 272 px x 16 B (s_conv4 with two tiles)
+
+struct LBSmem {
+  uint8_t A[LB_A_MAX];
+  uint8_t B[LR_STAGES][LR_B_MAX];
+  float bias[64];
+  uint64_t a_full, full[LR_STAGES], empty[LR_STAGES], d_full;
+  uint32_t tmem_base;
+};
+
+template <int EPI, int TILES>
+__global__ void __launch_bounds__(G_THREADS, 1)
+k_leg_batched_tc(LegArgs g, int n_mma, int* __restrict__ err) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  LBSmem& S = *reinterpret_cast<LBSmem*>(smem_raw);
+  constexpr int WIN = TILES * 128 + 16;             // pixels per window plane (kw <= 15)
+  constexpr uint32_t TMEM_COLS = TILES * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * (TILES * 128);
+  const int y = blockIdx.y, nh = blockIdx.z;
+  const int64_t in_base = (int64_t)(y / g.runs_per_img) * g.in_img_planes + (int64_t)(y % g.runs_per_img) * g.in_run_planes;
+  const int n_planes = g.kh * 2 * g.c8in;
+  const int n_slabs = g.kh * g.kw * 3;
+  const uint32_t b_bytes = (uint32_t)g.c8in * 64 * 16;
+  const int grp = (int)(LR_B_MAX / b_bytes) > 0 ? (int)(LR_B_MAX / b_bytes) : 1;      // slabs per ring stage
+  int nt = (int)((g.M - row0 + 127) / 128);         // tiles of this CTA that hold valid pixels
+  if (nt > TILES) nt = TILES;
+
+  if (tid == 0) {
+    mbar_init(&S.a_full, 1);
+    for (int s = 0; s < LR_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    mbar_init(&S.d_full, 1);
+    mbar_fence_init();
+  }
+  if (tid < 64) S.bias[tid] = (nh * 64 + tid < g.n_valid) ? g.bias[nh * 64 + tid] : 0.f;
+  if (warp == 2) tmem_alloc(&S.tmem_base, TMEM_COLS);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) mbar_arrive_expect_tx(&S.a_full, (uint32_t)n_planes * WIN * 16);
+    __syncwarp();
+    for (int pl = lane; pl < n_planes; pl += 32)
+      bulk_g2s(S.A + (size_t)pl * WIN * 16, g.A + ((size_t)(in_base + pl) * g.a_pitch + row0) * 8, WIN * 16, &S.a_full);
+    uint32_t s = 0, ph = 0;
+    for (int sl = 0; sl < n_slabs; sl += grp) {
+      const int cnt = (n_slabs - sl < grp) ? n_slabs - sl : grp;
+      TC_WAIT(&S.empty[s], ph ^ 1, 811);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&S.full[s], (uint32_t)cnt * b_bytes);
+        bulk_g2s(S.B[s], g.Bp + ((size_t)nh * n_slabs + sl) * (b_bytes / 2), (uint32_t)cnt * b_bytes, &S.full[s]);
+      }
+      __syncwarp();
+      if (++s == LR_STAGES) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_f16(128, n_mma);
+    const bool leader = elect_one() != 0;
+    const uint64_t ad0 = make_desc_kmajor_noswizzle(smem_u32(S.A), WIN * 16, 128);
+    const uint64_t bd0 = make_desc_kmajor_noswizzle(smem_u32(S.B[0]), 64 * 16, 128);
+    const uint32_t ad_hi = (uint32_t)(ad0 >> 32), ad_lo = (uint32_t)ad0;
+    const uint32_t bd_hi = (uint32_t)(bd0 >> 32), bd_lo = (uint32_t)bd0;
+    TC_WAIT(&S.a_full, 0, 812);
+    uint32_t sg = 0, ph = 0, first = 1;
+    int term = 0, dw = 0, dh = 0;                   // slab = (dh, dw, term); x*w ~= xh*wh + xl*wh + xh*wl
+#pragma unroll 1
+    for (int sl = 0; sl < n_slabs; sl += grp) {
+      const int cnt = (n_slabs - sl < grp) ? n_slabs - sl : grp;
+      TC_WAIT(&S.full[sg], ph, 813);
+      fence_after_sync();
+      for (int j = 0; j < cnt; ++j) {
+        if (leader) {
+          const uint32_t kind = (term == 1) ? 1u : 0u;
+          const uint32_t a_k = ad_lo + ((((dh * 2 + kind) * g.c8in) * (WIN * 16) + dw * 16) >> 4);
+          const uint32_t b_k = bd_lo + ((sg * LR_B_MAX + j * b_bytes) >> 4);
+          for (int c16 = 0; c16 < g.c8in / 2; ++c16) {
+            const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_k + ((c16 * 2 * (64 * 16)) >> 4));
+            const uint32_t a_c = a_k + ((c16 * 2 * (WIN * 16)) >> 4);
+#pragma unroll
+            for (int t = 0; t < TILES; ++t) {
+              if (t < nt) {
+                const uint64_t ad = ((uint64_t)ad_hi << 32) | (uint64_t)(a_c + ((t * 128 * 16) >> 4));
+                mma_ss(tmem + t * 64, ad, bd, idesc, first ? 0u : 1u);
+              }
+            }
+            first = 0;
+          }
+        }
+        first = 0;
+        if (++term == 3) { term = 0; if (++dw == g.kw) { dw = 0; ++dh; } }
+      }
+      if (leader) commit(&S.empty[sg]);
+      __syncwarp();
+      if (++sg == LR_STAGES) { sg = 0; ph ^= 1; }
+    }
+    if (leader) commit(&S.d_full);
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    TC_WAIT(&S.d_full, 0, 814);
+    fence_after_sync();
+#pragma unroll 1
+    for (int t = 0; t < nt; ++t) {
+      const int64_t r = row0 + t * 128 + q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        if (nh * 64 + c0 >= g.n_valid) break;         // warp-uniform
+        uint32_t u[16];
+        tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * 64 + c0, u);
+        tmem_ld_wait();
+        if (r < g.M) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(u[j]);
+          if (EPI == 4) {
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {
+              uint32_t phh[4], pll[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int n = c0 + h8 * 8 + 2 * j;
+                const float a = fmaxf(v[h8 * 8 + 2 * j] + S.bias[n], 0.f);
+                const float b = fmaxf(v[h8 * 8 + 2 * j + 1] + S.bias[n + 1], 0.f);
+                const __half2 hi = __floats2half2_rn(a, b);
+                const float2 hf = __half22float2(hi);
+                const __half2 lo = __floats2half2_rn(a - hf.x, b - hf.y);
+                phh[j] = *reinterpret_cast<const uint32_t*>(&hi);
+                pll[j] = *reinterpret_cast<const uint32_t*>(&lo);
+              }
+              const int c8 = nh * 8 + (c0 >> 3) + h8;
+              const int64_t plane = (int64_t)y * g.out_run_planes + c8;
+              *reinterpret_cast<uint4*>(g.out_planes + ((size_t)plane * g.out_pitch + r) * 8) = make_uint4(phh[0], phh[1], phh[2], phh[3]);
+              *reinterpret_cast<uint4*>(g.out_planes + ((size_t)(plane + g.out_run_planes / 2) * g.out_pitch + r) * 8) =
+                  make_uint4(pll[0], pll[1], pll[2], pll[3]);
+            }
+          } else {
+            float* dst = g.out_f32 + ((size_t)y * g.M + r) * g.n_valid + nh * 64 + c0;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              float4 o;
+              o.x = fmaxf(v[j4 * 4 + 0] + S.bias[c0 + j4 * 4 + 0], 0.f);
+              o.y = fmaxf(v[j4 * 4 + 1] + S.bias[c0 + j4 * 4 + 1], 0.f);
+              o.z = fmaxf(v[j4 * 4 + 2] + S.bias[c0 + j4 * 4 + 2], 0.f);
+              o.w = fmaxf(v[j4 * 4 + 3] + S.bias[c0 + j4 * 4 + 3], 0.f);
+              reinterpret_cast<float4*>(dst)[j4] = o;
+            }
+          }
+        }
+      }
+    }
+  }
+done:
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Correlation (yaw) head on tensor cores.
 //   G = L R^T (360 x 360, K = 128), corr[k] = sum_j G[(k + j + 180) mod 360, j]
 //   (RangePadding2D.py:34 + NormalizedCorrelation2D.py:96-109), yaw = 180 - argmax (infer.py:158).
@@ -1250,9 +1227,9 @@ done:
 // accumulated in fp32 in TMEM: three tcgen05.mma per K16 step, fp32-grade result, still < 5 % of
 // c_conv1's tensor time.  One CTA owns one half of R's rows (N = 192, zero-padded past 360) for all
 // of its pairs; L arrives as 32 KB stages (row tile x K half, hi+lo) through a 3-deep bulk-copy
-// ring.  The diagonal sums never touch memory: each epilogue warp reads its 32 rows of a finished
-// 128 x 192 tile from TMEM and rotates a running accumulator across lanes (bin(lane, col+1) ==
-// bin(lane-1, col)), flushing one finished bin per column.
+// ring.  The diagonal sums never touch memory: eight epilogue warps read 32-row x 32-column chunks of a
+// finished 128 x 192 tile from TMEM and sum along the diagonals with two lane reduce-scatters whose send
+// register absorbs the per-lane rotation (see the epilogue below); partial bins live in shared memory.
 // ------------------------------------------------------------------------------------------------
 constexpr int C6_THREADS = 384;            // warps 0-2: loader, MMA issuer, TMEM owner; warps 4-11: epilogue (2 per TMEM lane quarter)
 constexpr int C6_STAGES = 3;
@@ -1623,12 +1600,96 @@ k_dense_finalize(const float* __restrict__ partial, const float* __restrict__ bd
 // Leg layer 1 (5x15 stride (2,2), C_in = 4..25 -> 16, ReLU) straight from the fp32 NHWC input
 // image to the hi/lo fp16 planes layer 2 reads.  K = kh*kw*C_in is only 300 for the geometric cues
 // and N = 16: as a 64x64-tiled SIMT GEMM this took 61 us of a 245 us single-scan leg.  One thread
-// per (output pixel, 8 output channels); weights live in shared memory and are read by broadcast.
+// per TWO adjacent output pixels x all 16 output channels: the 16 weights of a (tap, channel) are read
+// once from shared memory (4 broadcast LDS.128) and feed 32 FFMAs -- the first version (one pixel x 8
+// channels per thread: 8 LDS per 32 FFMA) was bound by the load/store unit (profiles/r2_leg_batched.txt).
+template <bool CIN4>
+__global__ void __launch_bounds__(512)
+k_leg_layer1_direct(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                    int n, int H_in, int W_in, int cin, int kh, int kw, int sh, int sw, int H_out, int W_out,
+                    int relu, __half* __restrict__ out) {
+  constexpr int CO = 16;                                     // generateNet.py:161-164
+  extern __shared__ __align__(16) float w_s[];              // [kw*cin][16]: the taps of ONE kernel row at a time
+  const int pairs = (W_out + 1) / 2;                        //   (C_in = 25: 24 KB instead of 120 KB -> 4x the occupancy)
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;            // (img, y, pixel pair)
+  const bool active = idx < (int64_t)n * H_out * pairs;
+  if (!active) idx = 0;                                     // idle threads still take part in the barriers
+  const int xo = 2 * (int)(idx % pairs);
+  const int64_t r = idx / pairs;                                          // img*H_out + y
+  const int y = (int)(r % H_out);
+  const int64_t img = r / H_out;
+  const bool has1 = xo + 1 < W_out;
+  float acc0[CO], acc1[CO];
+#pragma unroll
+  for (int e = 0; e < CO; ++e) acc0[e] = acc1[e] = bias[e];
+  const float* base0 = x + ((img * H_in + (int64_t)y * sh) * W_in + (int64_t)xo * sw) * cin;
+  const float* base1 = has1 ? base0 + (int64_t)sw * cin : base0;         // a lone last pixel is computed twice
+  for (int dh = 0; dh < kh; ++dh) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kw * cin * CO; i += blockDim.x) w_s[i] = w[(size_t)dh * kw * cin * CO + i];
+    __syncthreads();
+    for (int dw = 0; dw < kw; ++dw) {
+      const int64_t off = ((int64_t)dh * W_in + dw) * cin;
+      const float* pw = w_s + (size_t)(dw * cin) * CO;
+      if (CIN4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(base0 + off));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(base1 + off));
+        const float va[4] = {a.x, a.y, a.z, a.w}, vb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 wv = *reinterpret_cast<const float4*>(pw + c * CO + q4 * 4);
+            acc0[q4 * 4 + 0] = fmaf(va[c], wv.x, acc0[q4 * 4 + 0]); acc1[q4 * 4 + 0] = fmaf(vb[c], wv.x, acc1[q4 * 4 + 0]);
+            acc0[q4 * 4 + 1] = fmaf(va[c], wv.y, acc0[q4 * 4 + 1]); acc1[q4 * 4 + 1] = fmaf(vb[c], wv.y, acc1[q4 * 4 + 1]);
+            acc0[q4 * 4 + 2] = fmaf(va[c], wv.z, acc0[q4 * 4 + 2]); acc1[q4 * 4 + 2] = fmaf(vb[c], wv.z, acc1[q4 * 4 + 2]);
+            acc0[q4 * 4 + 3] = fmaf(va[c], wv.w, acc0[q4 * 4 + 3]); acc1[q4 * 4 + 3] = fmaf(vb[c], wv.w, acc1[q4 * 4 + 3]);
+          }
+        }
+      } else {
+        for (int c = 0; c < cin; ++c) {
+          const float va = __ldg(base0 + off + c), vb = __ldg(base1 + off + c);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 wv = *reinterpret_cast<const float4*>(pw + c * CO + q4 * 4);
+            acc0[q4 * 4 + 0] = fmaf(va, wv.x, acc0[q4 * 4 + 0]); acc1[q4 * 4 + 0] = fmaf(vb, wv.x, acc1[q4 * 4 + 0]);
+            acc0[q4 * 4 + 1] = fmaf(va, wv.y, acc0[q4 * 4 + 1]); acc1[q4 * 4 + 1] = fmaf(vb, wv.y, acc1[q4 * 4 + 1]);
+            acc0[q4 * 4 + 2] = fmaf(va, wv.z, acc0[q4 * 4 + 2]); acc1[q4 * 4 + 2] = fmaf(vb, wv.z, acc1[q4 * 4 + 2]);
+            acc0[q4 * 4 + 3] = fmaf(va, wv.w, acc0[q4 * 4 + 3]); acc1[q4 * 4 + 3] = fmaf(vb, wv.w, acc1[q4 * 4 + 3]);
+          }
+        }
+      }
+    }
+  }
+  if (!active) return;
+  // [img][y][hi,lo][c8 = 2][x][8]
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    if (p == 1 && !has1) break;
+    const float* acc = p ? acc1 : acc0;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      __half hi[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float v = relu ? fmaxf(acc[g * 8 + e], 0.f) : acc[g * 8 + e];
+        hi[e] = __float2half_rn(v);
+        lo[e] = __float2half_rn(v - __half2float(hi[e]));
+      }
+      const int64_t plane_hi = r * 4 + g;
+      *reinterpret_cast<uint4*>(out + ((size_t)plane_hi * W_out + xo + p) * 8) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(out + ((size_t)(plane_hi + 2) * W_out + xo + p) * 8) = *reinterpret_cast<const uint4*>(lo);
+    }
+  }
+}
+
 template <bool CIN4>
 __global__ void __launch_bounds__(256)
-k_leg_layer1_direct(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+k_leg_layer1_small(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                     int n, int H_in, int W_in, int cin, int kh, int kw, int sh, int sw, int H_out, int W_out, int cout,
                     int relu, __half* __restrict__ out) {
+  // latency-mode variant (1-2 scans): one thread per (pixel, 8 output channels) -- four times the threads of
+  // k_leg_layer1_direct, which matters when a single scan has to fill 148 SMs
   extern __shared__ __align__(16) float w_s[];              // [kh*kw*cin][cout]
   for (int i = threadIdx.x; i < kh * kw * cin * cout; i += blockDim.x) w_s[i] = w[i];
   __syncthreads();
@@ -1700,10 +1761,7 @@ void tc_free(ovn_handle* h) {
                   t->mu_o1, t->mu_x3, t->b2base, t->b3eff};
   for (void* b : bufs) if (b) cudaFree(b);
   for (int l = 0; l < kMaxLegLayers; ++l) {
-    if (t->wleg[l]) cudaFree(t->wleg[l]);
     if (t->wres[l]) cudaFree(t->wres[l]);
-    if (t->leg_plane[l]) cudaFree(t->leg_plane[l]);
-    if (t->leg_shift[l]) cudaFree(t->leg_shift[l]);
   }
   if (t->pb_l16) cudaFree(t->pb_l16);
   if (t->pb_lc) cudaFree(t->pb_lc);
@@ -1793,42 +1851,20 @@ int tc_pack_weights(ovn_handle* h) {
   if ((rc = upload_vec(h, &t->w1p, p1)) != OVN_OK) return rc;
   if ((rc = upload_vec(h, &t->w2p, p2)) != OVN_OK) return rc;
   if ((rc = upload_vec(h, &t->w3p, p3)) != OVN_OK) return rc;
-  // ---- leg layers 2.. : copy e = (dh, dw, c8) -> plane dh*C8in + c8 of the run, row shift dw
+  // ---- leg layers 2.. : resident-activation layout of the weights.  Three-term split product
+  // x*w ~= xh*wh + xl*wh + xh*wl  (x = xh + xl, w = wh + wl in fp16): slab = (dh, dw, term)
   size_t max_planes_bytes = 0;
   for (int l = 0; l < h->n_leg; ++l) {
     const ConvSpec& L = h->leg[l];
     const size_t out_bytes = (size_t)L.h_out * 2 * (L.cout / 8) * L.w_out * 16;   // hi + lo planes
     if (out_bytes > max_planes_bytes) max_planes_bytes = out_bytes;
     if (l == 0) continue;
-    if (L.cin % 8 != 0 || L.cout % 8 != 0 || L.sw != 1 || L.w_out > 512)
+    if (L.cin % 16 != 0 || L.cout % 8 != 0 || L.sw != 1 || L.kw > 16)
       OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "tensor-core leg: layer %s shape not supported", L.name);
     const LayerWeights& w = h->host_w[L.name];
-    // three-term split product  x*w ~= xh*wh + xl*wh + xh*wl  (x = xh + xl, w = wh + wl in fp16):
-    // every (dh, dw, c8) tap becomes three copies (A plane hi/lo/hi, B rows wh/wh/wl)
-    const int c8in = L.cin / 8, nt = L.cout > 64 ? 128 : 64;
-    const int E0 = L.kh * L.kw * c8in, E = 3 * E0, n_slabs = (E + 3) / 4;
-    std::vector<int> cp(n_slabs * 4, 0), cs(n_slabs * 4, 0);
-    std::vector<__half> bp((size_t)n_slabs * 4 * nt * 8, __float2half(0.f));
-    for (int e0 = 0; e0 < E0; ++e0) {
-      const int c8 = e0 % c8in, dw = (e0 / c8in) % L.kw, dh = e0 / (c8in * L.kw);
-      for (int term = 0; term < 3; ++term) {
-        const int e = e0 * 3 + term;
-        cp[e] = dh * (2 * c8in) + (term == 1 ? c8in : 0) + c8;      // planes per input row: [hi c8in][lo c8in]
-        cs[e] = dw;
-        for (int n = 0; n < L.cout; ++n)
-          for (int k = 0; k < 8; ++k) {
-            const float wf = w.kernel[(((size_t)dh * L.kw + dw) * L.cin + c8 * 8 + k) * L.cout + n];
-            const __half wh = __float2half(wf);
-            const __half wl = __float2half(wf - __half2float(wh));
-            bp[((size_t)e * nt + n) * 8 + k] = (term == 2) ? wl : wh;
-          }
-      }
-    }
+    const int c8in = L.cin / 8;
     const int nz = (L.cout + 63) / 64;
-    t->leg_slabs[l] = n_slabs;
-    t->leg_nt[l] = nt;
     int rc2;
-    if ((rc2 = upload_vec(h, &t->wleg[l], bp)) != OVN_OK) return rc2;
     {
       // resident-activation layout: slab = (dh, dw, term), rows = all C_in/8 chunks, 64 output channels
       const int nsl = L.kh * L.kw * 3;
@@ -1849,8 +1885,6 @@ int tc_pack_weights(ovn_handle* h) {
             }
       if ((rc2 = upload_vec(h, &t->wres[l], br)) != OVN_OK) return rc2;
     }
-    if ((rc2 = upload_vec(h, &t->leg_plane[l], cp)) != OVN_OK) return rc2;
-    if ((rc2 = upload_vec(h, &t->leg_shift[l], cs)) != OVN_OK) return rc2;
   }
   for (int b = 0; b < 2; ++b) {
     const size_t bytes = max_planes_bytes * h->cfg.max_batch_scans + 32768;   // + tile overrun slack
@@ -1879,16 +1913,14 @@ int tc_pack_weights(ovn_handle* h) {
   OVN_CUDA(h, cudaMemset(t->x3, 0, (size_t)16 * t->rows_pad * 8 * sizeof(__half)));
   OVN_CUDA(h, cudaFuncSetAttribute(k_delta_conv1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem)));
   OVN_CUDA(h, cudaFuncSetAttribute(k_conv2_sw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(C2Smem)));
-#define OVN_GEMM_ATTR(E, N, T)                                                                                  \
-  OVN_CUDA(h, cudaFuncSetAttribute(k_gemm_stream_tc<E, N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                   (int)sizeof(GSmem<N, T>)))
   OVN_CUDA(h, cudaFuncSetAttribute(k_conv3_resident_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(C3Smem)));
-  OVN_GEMM_ATTR(4, 64, 4); OVN_GEMM_ATTR(4, 128, 4); OVN_GEMM_ATTR(3, 128, 4);
-  OVN_CUDA(h, cudaFuncSetAttribute(k_leg_layer1_direct<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  OVN_CUDA(h, cudaFuncSetAttribute(k_leg_layer1_direct<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  OVN_CUDA(h, cudaFuncSetAttribute(k_leg_layer1_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  OVN_CUDA(h, cudaFuncSetAttribute(k_leg_layer1_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   OVN_CUDA(h, cudaFuncSetAttribute(k_leg_resident_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LRSmem)));
   OVN_CUDA(h, cudaFuncSetAttribute(k_leg_resident_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LRSmem)));
-#undef OVN_GEMM_ATTR
+#define OVN_LB_ATTR(E, T) OVN_CUDA(h, cudaFuncSetAttribute(k_leg_batched_tc<E, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LBSmem)))
+  OVN_LB_ATTR(3, 1); OVN_LB_ATTR(3, 2); OVN_LB_ATTR(3, 4); OVN_LB_ATTR(4, 1); OVN_LB_ATTR(4, 2); OVN_LB_ATTR(4, 4);
+#undef OVN_LB_ATTR
   return OVN_OK;
 }
 
@@ -1916,24 +1948,34 @@ k_nhwc_to_planes(const float* __restrict__ x, int64_t total_chunks, int H, int W
 }
 
 int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cudaStream_t s) {
-  // layer 1 (C_in = 4..25, stride (2,2)) stays on the fp32 SIMT kernel; layers 2..10 run on
-  // k_gemm_stream_tc over C8-interleaved fp16 activation planes: one CTA per output image row,
-  // the kw taps are row shifts of the bulk copies, the kh taps select the input row's planes.
+  // layer 1 (C_in = 4..25, stride (2,2), N = 16) runs on the direct SIMT kernel and writes hi/lo fp16
+  // C8-interleaved planes; layers 2.. run on tcgen05 with the activation window resident in shared
+  // memory (kw taps = descriptor row offsets, kh taps = the input rows' planes).
   TcState* t = h->tc;
   if (!t) OVN_SET_ERR(h, OVN_ERR_WEIGHTS, "tensor-core weights not packed");
   prof_mark(h, PROF_LEG, s);
   {
     const ConvSpec& L = h->leg[0];
     const int64_t chunks = (int64_t)n * L.h_out * (L.cout / 8) * L.w_out;
-    const size_t w_bytes = (size_t)L.kh * L.kw * L.cin * L.cout * sizeof(float);
-    if (w_bytes <= 200 * 1024 && L.cout % 8 == 0) {
+    const size_t w_bytes = (size_t)L.kw * L.cin * L.cout * sizeof(float);        // one kernel row of taps
+    const size_t w_all = w_bytes * L.kh;
+    if (n <= 2 && w_all <= 200 * 1024 && L.cout % 8 == 0) {
       const unsigned grid = (unsigned)((chunks + 255) / 256);
       if (L.cin == 4)
-        k_leg_layer1_direct<true><<<grid, 256, w_bytes, s>>>(d_input, h->d_w[0], h->d_b[0], n, L.h_in, L.w_in, L.cin, L.kh, L.kw,
-                                                            L.sh, L.sw, L.h_out, L.w_out, L.cout, L.relu, t->actp[0]);
+        k_leg_layer1_small<true><<<grid, 256, w_all, s>>>(d_input, h->d_w[0], h->d_b[0], n, L.h_in, L.w_in, L.cin, L.kh, L.kw,
+                                                         L.sh, L.sw, L.h_out, L.w_out, L.cout, L.relu, t->actp[0]);
       else
-        k_leg_layer1_direct<false><<<grid, 256, w_bytes, s>>>(d_input, h->d_w[0], h->d_b[0], n, L.h_in, L.w_in, L.cin, L.kh, L.kw,
-                                                             L.sh, L.sw, L.h_out, L.w_out, L.cout, L.relu, t->actp[0]);
+        k_leg_layer1_small<false><<<grid, 256, w_all, s>>>(d_input, h->d_w[0], h->d_b[0], n, L.h_in, L.w_in, L.cin, L.kh, L.kw,
+                                                          L.sh, L.sw, L.h_out, L.w_out, L.cout, L.relu, t->actp[0]);
+    } else if (w_bytes <= 48 * 1024 && L.cout == 16) {
+      const int64_t work = (int64_t)n * L.h_out * ((L.w_out + 1) / 2);          // one thread per pixel pair
+      const unsigned grid = (unsigned)((work + 511) / 512);
+      if (L.cin == 4)
+        k_leg_layer1_direct<true><<<grid, 512, w_bytes, s>>>(d_input, h->d_w[0], h->d_b[0], n, L.h_in, L.w_in, L.cin, L.kh, L.kw,
+                                                            L.sh, L.sw, L.h_out, L.w_out, L.relu, t->actp[0]);
+      else
+        k_leg_layer1_direct<false><<<grid, 512, w_bytes, s>>>(d_input, h->d_w[0], h->d_b[0], n, L.h_in, L.w_in, L.cin, L.kh, L.kw,
+                                                             L.sh, L.sw, L.h_out, L.w_out, L.relu, t->actp[0]);
     } else {
       int rc = leg_layer_fp32(h, 0, d_input, h->d_act[0], n, s);
       if (rc != OVN_OK) return rc;
@@ -1946,27 +1988,22 @@ int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cuda
   for (int l = 1; l < h->n_leg; ++l) {
     const ConvSpec& L = h->leg[l];
     const bool last = (l == h->n_leg - 1);
-    GemmArgs a = {};
-    a.A = t->actp[cur]; a.a_pitch = L.w_in;
-    a.copy_plane = t->leg_plane[l]; a.copy_shift = t->leg_shift[l]; a.n_slabs = t->leg_slabs[l];
-    a.Bp = t->wleg[l]; a.bias = h->d_b[l]; a.M = L.w_out;
-    a.runs_per_img = L.h_out; a.in_img_planes = L.h_in * 2 * (L.cin / 8); a.in_run_planes = L.sh * 2 * (L.cin / 8);
-    a.out_planes = t->actp[cur ^ 1]; a.out_pitch = L.w_out; a.out_run_planes = 2 * (L.cout / 8);
-    a.out_f32 = d_fv;
-    a.n_valid = L.cout;
-    // latency mode (few scans): one 128-row tile and one 64-channel slice per CTA, 12-deep ring;
-    // throughput mode (batched encode): four tiles per CTA share every weight slab
-    const bool latency = (int64_t)n * L.h_out * 4 <= h->sm_count;
+    // latency mode (1-2 scans): one 128-pixel tile and one 64-channel slice per CTA, K split over CTAs;
+    // throughput mode (batched encode): TILES tiles per CTA share every streamed weight slab
+    const int tiles_x = (L.w_out + 127) / 128, nz = (L.cout + 63) / 64;
+    const int base_ctas = tiles_x * n * L.h_out * nz;
+    const bool latency = base_ctas * 2 <= h->sm_count;
     if (last && (L.cout != 128 || L.h_out != 1)) OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "tensor-core leg: unexpected last layer");
+    LegArgs la = {};
+    la.A = t->actp[cur]; la.a_pitch = L.w_in; la.runs_per_img = L.h_out; la.in_img_planes = L.h_in * 2 * (L.cin / 8);
+    la.in_run_planes = L.sh * 2 * (L.cin / 8); la.kh = L.kh; la.kw = L.kw; la.c8in = L.cin / 8; la.Bp = t->wres[l];
+    la.bias = h->d_b[l]; la.n_valid = L.cout; la.M = L.w_out; la.out_planes = t->actp[cur ^ 1]; la.out_pitch = L.w_out;
+    la.out_run_planes = 2 * (L.cout / 8); la.out_f32 = d_fv;
+    la.n_split = 1; la.part = t->leg_part; la.counters = t->leg_counters;
     if (latency) {
-      dim3 grid((unsigned)((L.w_out + 127) / 128), (unsigned)(n * L.h_out), (unsigned)((L.cout + 63) / 64));
-      LegArgs la = {};
-      la.A = a.A; la.a_pitch = a.a_pitch; la.runs_per_img = a.runs_per_img; la.in_img_planes = a.in_img_planes;
-      la.in_run_planes = a.in_run_planes; la.kh = L.kh; la.kw = L.kw; la.c8in = L.cin / 8; la.Bp = t->wres[l];
-      la.bias = h->d_b[l]; la.n_valid = L.cout; la.M = L.w_out; la.out_planes = a.out_planes; la.out_pitch = a.out_pitch;
-      la.out_run_planes = a.out_run_planes; la.out_f32 = d_fv;
+      dim3 grid((unsigned)tiles_x, (unsigned)(n * L.h_out), (unsigned)nz);
       // split-K so that a layer's CTAs roughly fill the GPU
-      const int base_ctas = (int)(grid.x * grid.y * grid.z), n_slabs_l = L.kh * L.kw * 3;
+      const int n_slabs_l = L.kh * L.kw * 3;
       // measured (single scan, whole leg): >= 1 / 2 / 3 / 4 / 6 / 9 / 18 slabs per split ->
       // 0.196 / 0.165 / 0.151 / 0.144 / 0.138 / 0.152 / 0.154 ms; filling the GPU twice over is worse
       constexpr int kMinSlabsPerSplit = 6;
@@ -1974,7 +2011,7 @@ int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cuda
       if (n_split > n_slabs_l / kMinSlabsPerSplit) n_split = n_slabs_l / kMinSlabsPerSplit;
       if (n_split > kLegPartTiles / base_ctas) n_split = kLegPartTiles / base_ctas;
       if (n_split < 1) n_split = 1;
-      la.n_split = n_split; la.part = t->leg_part; la.counters = t->leg_counters;
+      la.n_split = n_split;
       grid.z *= n_split;
       cudaLaunchConfig_t lc = {};
       lc.gridDim = grid; lc.blockDim = dim3(G_THREADS); lc.dynamicSmemBytes = sizeof(LRSmem); lc.stream = s;
@@ -1985,10 +2022,21 @@ int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cuda
       if (last) OVN_CUDA(h, cudaLaunchKernelEx(&lc, k_leg_resident_tc<3>, la, h->d_err));
       else OVN_CUDA(h, cudaLaunchKernelEx(&lc, k_leg_resident_tc<4>, la, h->d_err));
     } else {
-      const dim3 grid(1, (unsigned)(n * L.h_out), 1);
-      if (last) k_gemm_stream_tc<3, 128, 4><<<grid, G_THREADS, sizeof(GSmem<128, 4>), s>>>(a, h->d_err);
-      else if (t->leg_nt[l] == 128) k_gemm_stream_tc<4, 128, 4><<<grid, G_THREADS, sizeof(GSmem<128, 4>), s>>>(a, h->d_err);
-      else k_gemm_stream_tc<4, 64, 4><<<grid, G_THREADS, sizeof(GSmem<64, 4>), s>>>(a, h->d_err);
+      // largest tile count whose activation window fits and that still gives every SM a CTA
+      int T = 1;
+      for (int cand = 4; cand >= 2; cand >>= 1) {
+        const size_t win_bytes = (size_t)L.kh * 2 * (L.cin / 8) * (cand * 128 + 16) * 16;
+        const int ctas = ((L.w_out + cand * 128 - 1) / (cand * 128)) * n * L.h_out * nz;
+        if (win_bytes <= (size_t)LB_A_MAX && ctas >= h->sm_count) { T = cand; break; }
+      }
+      if ((size_t)L.kh * 2 * (L.cin / 8) * (128 + 16) * 16 > (size_t)LB_A_MAX)
+        OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "tensor-core leg: layer %s window does not fit shared memory", L.name);
+      const dim3 grid((unsigned)((L.w_out + T * 128 - 1) / (T * 128)), (unsigned)(n * L.h_out), (unsigned)nz);
+      int n_mma = L.cout >= 64 ? 64 : ((L.cout + 15) / 16) * 16;          // MMA N (multiple of 16 for M = 128)
+#define OVN_LEG_BATCHED(E, TT) k_leg_batched_tc<E, TT><<<grid, G_THREADS, sizeof(LBSmem), s>>>(la, n_mma, h->d_err)
+      if (last) { if (T == 4) OVN_LEG_BATCHED(3, 4); else if (T == 2) OVN_LEG_BATCHED(3, 2); else OVN_LEG_BATCHED(3, 1); }
+      else { if (T == 4) OVN_LEG_BATCHED(4, 4); else if (T == 2) OVN_LEG_BATCHED(4, 2); else OVN_LEG_BATCHED(4, 1); }
+#undef OVN_LEG_BATCHED
     }
     OVN_LAUNCH_CHECK(h);
     cur ^= 1;

@@ -234,3 +234,25 @@ def test_single_scan_leg_is_bit_reproducible_and_matches_batched():
   assert np.abs(b.cpu().numpy() - ref).max() / scale <= 4e-3
   assert (a - b).abs().max().item() / scale <= 1e-4
   eng1.close(); eng6.close()
+
+
+def test_batched_leg_matches_oracle_and_single_scan_path():
+  """Throughput-mode leg (k_leg_batched_tc: resident activation windows, several tiles per CTA) on a
+  batch large enough that every layer takes that path, against the float64 oracle and against the
+  latency-mode (single-scan, split-K) path of the same weights."""
+  w = N.glorot_weights(4, MODEL, seed=6)
+  x = synth.range_like_images(31, 20, 4)
+  ref = N.leg_forward(x, w, MODEL)[:, 0]
+  scale = np.abs(ref).max()
+  eng = Engine(model=MODEL, precision='f16_tc', max_batch_scans=20, max_batch_pairs=1)
+  eng1 = Engine(model=MODEL, precision='f16_tc', max_batch_scans=1, max_batch_pairs=1)
+  eng.load_weights(w); eng1.load_weights(w)
+  xt = torch.from_numpy(x).to(eng.device)
+  a = eng.leg(xt)
+  b = eng1.leg(xt)
+  assert torch.equal(eng.leg(xt), a)                                   # bit-reproducible
+  err = np.abs(a.cpu().numpy() - ref).max() / scale
+  print('\n[parity] batched leg f16_tc (hi/lo split operands): max rel err vs float64 oracle = %.3e' % err)
+  assert err <= 1e-4
+  assert (a - b).abs().max().item() / scale <= 1e-4
+  eng.close(); eng1.close()
