@@ -251,7 +251,9 @@ class Infer():
     depth, normal, probabilities, intensity; raw values."""
     H, W = self.inputShape[0], self.inputShape[1]
     x = np.zeros((len(filenames), H, W, self.no_input_channels), dtype=np.float32)
-    for i, name in enumerate(filenames):
+
+    def load_one(i_name):
+      i, name = i_name
       c = 0
       if self.use_depth:
         x[i, :, :, c] = self._load_cue('depth', name, 'depth')
@@ -269,6 +271,16 @@ class Infer():
       if self.use_intensity:
         x[i, :, :, c] = self._load_cue('intensity', name, 'intensity')
         c += 1
+
+    if len(filenames) <= 1:
+      for item in enumerate(filenames):
+        load_one(item)
+    else:
+      # the reference feeds predict_generator with 8 workers (infer.py:262); np.load releases the GIL in its
+      # file reads, so a small thread pool keeps the GPU fed when thousands of scans are encoded (testing.py)
+      from concurrent.futures import ThreadPoolExecutor
+      with ThreadPoolExecutor(max_workers=min(8, len(filenames))) as ex:
+        list(ex.map(load_one, enumerate(filenames)))     # list(): re-raise the first worker exception
     return x
 
   def _create_feature_volumes_device(self, filenames):

@@ -190,3 +190,71 @@ def test_lcd_on_bank_sharded_over_two_gpus(dataset, tmp_path):
     assert np.array_equal(got['ov_%d' % k], log[k][1])             # every rank calibrates on frame 0: bit-identical
     assert np.array_equal(got['yaw_%d' % k], log[k][2])
   assert sorted(found) == got['found_k'].tolist()
+
+
+def _search_worker(rank, world, port, out_path):
+  import torch.distributed as dist
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  torch.cuda.set_device(rank)
+  dev = torch.device('cuda', rank)
+  dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+  from overlapnet_b200.engine import Engine
+  from overlapnet_b200.search import ShardedSearch, engine_heads_fn, engine_rows_fn, shard_range
+  n_total = 13                                             # odd: shards of 7 and 6
+  bank_np = synth.feature_volumes(4, n_total)[:, 0]
+  w = N.glorot_weights(4, MODEL, seed=8)
+  eng = Engine(model=MODEL, precision='f16_tc', device=rank, max_batch_scans=1, max_batch_pairs=8)
+  eng.load_weights(w)
+  eng.calibrate(torch.from_numpy(bank_np[0]))              # the same numeric centres on every rank
+  lo, hi = shard_range(n_total, rank, world)
+  shard = torch.from_numpy(bank_np[lo:hi].copy()).to(dev)
+  res = {}
+  for transport in ('symm', 'collective'):
+    ss = ShardedSearch(engine_heads_fn(eng), shard, n_total, transport=transport)
+    assert ss.transport == transport
+    q = torch.from_numpy(bank_np[5].copy()).to(dev) if rank == 0 else torch.zeros((360, 128), device=dev)
+    for rep in range(3):                                   # repeated queries reuse the buffers / flags
+      r = ss.query(q)
+    if rank == 0:
+      res[transport] = (r[0].cpu().numpy(), r[1].cpu().numpy())
+    else:
+      assert r is None
+  ap = ss.all_pairs(rows_fn=engine_rows_fn(eng))
+  eng.check()
+  if rank == 0:
+    np.savez(out_path, symm_ov=res['symm'][0], symm_yaw=res['symm'][1], coll_ov=res['collective'][0],
+             coll_yaw=res['collective'][1], ap_ov=ap[0].cpu().numpy(), ap_yaw=ap[1].cpu().numpy())
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_sharded_search_and_all_pairs_on_two_gpus(tmp_path):
+  """ShardedSearch on NCCL / CUDA: the peer-memory transport ('symm': kernels read the query from and
+  write their results into rank 0's memory, own signal kernels) and the collective fallback give exactly
+  what one GPU computes; so do the all-pairs rows scored with ovn_heads_rows_vs_bank."""
+  if torch.cuda.device_count() < 2:
+    pytest.skip('needs 2 GPUs (gpurun --gpus 2)')
+  import torch.multiprocessing as mp
+  from overlapnet_b200.engine import Engine
+  out = str(tmp_path / 'search.npz')
+  mp.spawn(_search_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+  got = np.load(out)
+  n_total = 13
+  bank_np = synth.feature_volumes(4, n_total)[:, 0]
+  eng = Engine(model=MODEL, precision='f16_tc', max_batch_scans=1, max_batch_pairs=8)
+  eng.load_weights(N.glorot_weights(4, MODEL, seed=8))
+  eng.calibrate(torch.from_numpy(bank_np[0]))
+  bank = torch.from_numpy(bank_np).to(eng.device)
+  ov, yaw, _ = eng.heads_1vsN(bank, bank[5], n_cand=n_total)
+  for tag in ('symm', 'coll'):
+    assert np.array_equal(got[tag + '_ov'], ov.cpu().numpy()) and np.array_equal(got[tag + '_yaw'], yaw.cpu().numpy())
+  assert int(yaw[5]) == 0
+  ap_ov, ap_yaw = eng.heads_rows_vs_bank(bank, 0, n_total)
+  eng.check()
+  assert np.array_equal(got['ap_ov'], ap_ov.cpu().numpy()) and np.array_equal(got['ap_yaw'], ap_yaw.cpu().numpy())
+  # row i = query i against every candidate j (LEFT = bank[j], RIGHT = bank[i]); the head is not symmetric
+  o2, y2, _ = eng.heads(bank, torch.tensor([3, 7], dtype=torch.int32), torch.tensor([7, 3], dtype=torch.int32))
+  assert np.array_equal(ap_ov.cpu().numpy()[[7, 3], [3, 7]], o2.cpu().numpy())
+  assert np.array_equal(np.diag(ap_yaw.cpu().numpy()), np.zeros(n_total, np.int32))
+  eng.close()
