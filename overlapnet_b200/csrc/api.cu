@@ -585,8 +585,8 @@ int ovn_bank_prepare(ovn_handle* h, const float* d_bank, int64_t bank_capacity, 
 int ovn_peer_signal(ovn_handle* h, const uint64_t* h_flag_ptrs, int32_t n, int32_t value, void* stream) {
   if (!h) return OVN_ERR_INVALID_ARG;
   DeviceGuard guard(h);
-  REQUIRE(h, h_flag_ptrs != nullptr && n >= 0 && n <= 16, "bad peer list (at most 16 peers)");
   if (n == 0) return OVN_OK;
+  REQUIRE(h, h_flag_ptrs != nullptr && n > 0 && n <= 16, "bad peer list (at most 16 peers)");
   PeerPtrs pp = {};
   for (int i = 0; i < n; ++i) pp.p[i] = reinterpret_cast<int32_t*>(h_flag_ptrs[i]);
   k_peer_signal<<<1, 32, 0, (cudaStream_t)stream>>>(pp, n, value);
@@ -597,8 +597,8 @@ int ovn_peer_signal(ovn_handle* h, const uint64_t* h_flag_ptrs, int32_t n, int32
 int ovn_peer_wait(ovn_handle* h, const int32_t* d_flags, int32_t n, int32_t skip, int32_t value, void* stream) {
   if (!h) return OVN_ERR_INVALID_ARG;
   DeviceGuard guard(h);
-  REQUIRE(h, d_flags != nullptr && n >= 0 && n <= 32, "bad flag list");
   if (n == 0) return OVN_OK;
+  REQUIRE(h, d_flags != nullptr && n > 0 && n <= 32, "bad flag list");
   k_peer_wait<<<1, 32, 0, (cudaStream_t)stream>>>(d_flags, n, skip, value, h->d_err);
   OVN_LAUNCH_CHECK(h);
   return OVN_OK;

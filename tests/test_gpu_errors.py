@@ -120,3 +120,61 @@ def test_engine_on_non_current_device():
   eng.check()
   assert torch.isfinite(ov).all() and int(yaw[0]) == 0
   eng.close()
+
+
+def test_empty_and_degenerate_calls(bank_np):
+  """Empty candidate lists, empty row ranges and no-op calls return OVN_OK without launching work that
+  could fault (infer_multiple with [] returns None; infer_multiple_vs_multiple with [] too)."""
+  for prec in ('f16_tc', 'fp32'):
+    eng = Engine(model=MODEL, precision=prec, max_batch_scans=1, max_batch_pairs=8)
+    eng.load_weights(N.glorot_weights(4, MODEL, seed=0))
+    bank = torch.from_numpy(bank_np).to(eng.device)
+    empty = torch.zeros((0,), dtype=torch.int32)
+    ov, yaw, _ = eng.heads(bank, empty, empty)
+    assert ov.numel() == 0 and yaw.numel() == 0
+    ov, yaw, _ = eng.heads_1vsN(bank, bank[0], cand_idx=empty)
+    assert ov.numel() == 0
+    ov, yaw = eng.heads_rows_vs_bank(bank, 3, 3)
+    assert ov.shape == (0, 6)
+    fv = eng.leg(torch.zeros((0, 64, 900, 4), device=eng.device))
+    assert fv.shape == (0, 360, 128)
+    eng.calibrate(bank[1])                                   # no-op for fp32, explicit calibration for f16_tc
+    mu, is_set = eng.get_feature_center()
+    assert is_set == (prec == 'f16_tc')
+    eng.peer_signal([], 1)
+    eng.check()
+    ov, yaw, _ = eng.heads_1vsN(bank, bank[2], n_cand=6)     # the handle is fully usable afterwards
+    eng.check()
+    assert int(yaw[2]) == 0 and torch.isfinite(ov).all()
+    eng.close()
+
+
+def test_sharded_infer_without_process_group_is_infer(tmp_path):
+  """ShardedInfer with world size 1 (no process group) is the plain Infer: same numbers, same shapes."""
+  import copy
+  from overlapnet_b200 import weights as W
+  from overlapnet_b200.infer import Infer
+  from overlapnet_b200.sharded_infer import ShardedInfer
+  model = {'modelType': 'SiameseNetworkTemplate', 'legsType': '360OutputkLegs', 'overlap_head': 'DeltaLayerConv1NetworkHead',
+           'orientation_head': 'CorrelationHead', 'inputShape': [64, 900], 'leg_output_width': 360,
+           'strides_layer1': [2, 2], 'additional_unsymmetric_layer3a': True}
+  seq = tmp_path / '07'
+  (seq / 'depth').mkdir(parents=True)
+  (seq / 'normal').mkdir()
+  x = synth.range_like_images(3, 4, 4)
+  for i in range(4):
+    np.save(str(seq / 'depth' / ('%06d.npy' % i)), x[i, :, :, 0])
+    np.save(str(seq / 'normal' / ('%06d.npy' % i)), x[i, :, :, 1:4])
+  wpath = str(tmp_path / 'w.npz')
+  W.save_npz(wpath, N.glorot_weights(4, model, seed=2))
+  cfg = {'pretrained_weightsfilename': wpath, 'use_depth': True, 'use_normals': True, 'use_class_probabilities': False,
+         'use_class_probabilities_pca': False, 'use_intensity': False, 'data_root_folder': str(tmp_path),
+         'infer_seqs': '07', 'batch_size': 16, 'model': model}
+  a, b = Infer(copy.deepcopy(cfg)), ShardedInfer(copy.deepcopy(cfg))
+  for inf in (a, b):
+    assert inf.infer_multiple(0, []) is None and inf.infer_multiple(1, []) is None
+  ra, rb = a.infer_multiple(2, [0, 1]), b.infer_multiple(2, [0, 1])
+  assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]) and ra[0].shape == rb[0].shape == (2,)
+  ra, rb = a.infer_multiple(3, [1]), b.infer_multiple(3, [1])
+  assert ra[0].shape == rb[0].shape == () and float(ra[0]) == float(rb[0])
+  assert b.local_frames == [0, 1, 2, 3]

@@ -89,7 +89,7 @@ def emu_logit(L, R, w, v):
     mx = h(x3.mean((0, 1)))
     if v.get('w3_fold_exact', False):         # the mean's image under c_conv3 is folded with the fp32 weights
       x3_mean = mx
-      x3 = h(x3 - mx)
+      x3 = (x3 - mx) if v.get('x3_keep_exact', False) else h(x3 - mx)
     else:
       x3 = h(x3 - mx) + mx
   elif v.get('x3_16', True):
@@ -105,23 +105,29 @@ def emu_logit(L, R, w, v):
   return float(y @ Wd[:, 0] + bd[0])
 
 
+EX = dict(d16=False, w1_16=False, o1_16=False, w2_16=False, x3_16=False, w3_16=False)
 VARIANTS = [
-    ('all exact (sanity)', dict(fv='exact', d16=False, w1_16=False, o1_16=False, w2_16=False, x3_16=False, w3_16=False)),
-    ('current f16_tc', dict()),
-    ('only fv rounding', dict(fv='f16', d16=False, w1_16=False, o1_16=False, w2_16=False, x3_16=False, w3_16=False)),
-    ('only |d| rounding', dict(fv='exact', d16=True, w1_16=False, o1_16=False, w2_16=False, x3_16=False, w3_16=False)),
-    ('only W1', dict(fv='exact', d16=False, w1_16=True, o1_16=False, w2_16=False, x3_16=False, w3_16=False)),
-    ('only o1', dict(fv='exact', d16=False, w1_16=False, o1_16=True, w2_16=False, x3_16=False, w3_16=False)),
-    ('only W2', dict(fv='exact', d16=False, w1_16=False, o1_16=False, w2_16=True, x3_16=False, w3_16=False)),
-    ('only x3', dict(fv='exact', d16=False, w1_16=False, o1_16=False, w2_16=False, x3_16=True, w3_16=False)),
-    ('only W3', dict(fv='exact', d16=False, w1_16=False, o1_16=False, w2_16=False, x3_16=False, w3_16=True)),
-    ('center + f16', dict(fv='center')),
-    ('hilo sub', dict(fv='hilo')),
-    ('hilo fma-chain', dict(fv='hilo_fma')),
-    ('R-side exact', dict(fv='r_exact')),
-    ('hilo, x3 exact', dict(fv='hilo', x3_16=False)),
-    ('hilo, x3+o1 exact', dict(fv='hilo', x3_16=False, o1_16=False)),
-    ('hilo, x3+o1+W2+W3 exact', dict(fv='hilo', x3_16=False, o1_16=False, w2_16=False, w3_16=False)),
+    ('all exact (sanity)', dict(fv='exact', **EX)),
+    ('round-1 f16_tc (all fp16)', dict()),
+    ('PRODUCTION r2: centres + W2 hi/lo', dict(fv='center', w2_16=False, o1_center=True, x3_center=True, w3_fold_exact=True)),
+    ('--- single terms (everything else exact) ---', None),
+    ('only fv fp16 (round 1)', dict(fv='f16', **EX)),
+    ('only fv fp16 CENTRED', dict(fv='center', **EX)),
+    ('only fv hi/lo subtraction', dict(fv='hilo', **EX)),
+    ('only |d| fp16', dict(fv='exact', **{**EX, 'd16': True})),
+    ('only W1 fp16', dict(fv='exact', **{**EX, 'w1_16': True})),
+    ('only o1 fp16', dict(fv='exact', **{**EX, 'o1_16': True})),
+    ('only o1 fp16 CENTRED', dict(fv='exact', **{**EX, 'o1_center': True})),
+    ('only W2 fp16 (round 1)', dict(fv='exact', **{**EX, 'w2_16': True})),
+    ('only x3 fp16', dict(fv='exact', **{**EX, 'x3_16': True})),
+    ('only x3 fp16 CENTRED + exact fold', dict(fv='exact', **{**EX, 'x3_center': True, 'w3_fold_exact': True})),
+    ('only W3 fp16 (x3 raw)', dict(fv='exact', **{**EX, 'w3_16': True})),
+    ('only W3 fp16 (x3 centred, exact fold)', dict(fv='exact', **{**EX, 'w3_16': True, 'x3_center': True, 'w3_fold_exact': True,
+                                                            'x3_keep_exact': True})),
+    ('--- what more would buy ---', None),
+    ('production + fv hi/lo', dict(fv='hilo', w2_16=False, o1_center=True, x3_center=True, w3_fold_exact=True)),
+    ('production + x3, o1 exact', dict(fv='center', w2_16=False, o1_16=False, x3_16=False)),
+    ('production + W3 exact', dict(fv='center', w2_16=False, o1_center=True, x3_center=True, w3_fold_exact=True, w3_16=False)),
 ]
 
 
@@ -161,6 +167,9 @@ def main():
   print('overlaps (ref) at spread %.2f: %s' % (args.spread, np.round(ov_ref, 3)))
   print('%-28s %12s %12s %12s' % ('variant', 'max|dz|/std', 'rms|dz|/std', 'max|d ov|'))
   for name, v in VARIANTS:
+    if v is None:
+      print(name)
+      continue
     if args.only and args.only not in name:
       continue
     z = np.array([emu_logit(Lb[a], Lb[b], w, v) for a, b in zip(left, right)])
