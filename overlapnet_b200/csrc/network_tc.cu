@@ -816,6 +816,198 @@ done:
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_conv3_pair_tc -- c_conv3 on CTA PAIRS (tcgen05 cta_group::2), round 2.
+// The single-CTA kernel above is bound by the shared-memory operand fetch of SS-mode MMAs (N = 128:
+// 111.8 clk per MMA against 64 ideal, profiles/r1_mma_rate_probe.txt; ncu: tensor pipe 64 % active).
+// A pair of CTAs on one TPC computes one M = 256 x N = 256 tile: each CTA holds the activation window of
+// its own 128 rows and only HALF of every weight slab (128 of the 256 output channels), so per MMA a CTA
+// fetches 4 KB + 4 KB for twice the work of the old 4 KB + 4 KB MMA; measured rate 133 clk per
+// M256 N256 K16 MMA = 0.96 of ideal (csrc/cta2_probe.cu, profiles/r2_cta2_probe.txt).  All 256 output
+// channels are produced at once (no second pass over the window), the L2 -> shared weight traffic per row
+// is unchanged.  Protocol: only the leader CTA (cluster rank 0) issues MMAs; tcgen05.commit multicasts
+// "slot free" / "accumulator full" to both CTAs' barriers; the peer's warp 1 relays "my operands have
+// landed" to the leader's barriers (remote mbarrier arrive); the peer's epilogue warps release the
+// accumulator on the leader's barrier.  Same MMA order as the single-CTA kernel: bit-identical results.
+// ------------------------------------------------------------------------------------------------
+constexpr int P3_ROWS = 128, P3_WIN = 192, P3_STAGES = 4;
+constexpr int P3_PLANE_BYTES = P3_WIN * 16;                 // 3072
+constexpr int P3_WIN_BYTES = C3_PLANES * P3_PLANE_BYTES;   // 49152
+constexpr int P3_B_BYTES = 4 * 4 * 128 * 16;                // one ring stage = this CTA's half of the FOUR K32 x N256 slabs of a tap
+                                                            //   (8 MMAs per barrier round trip: with one slab per stage the issuer's two ~90 clk
+                                                            //    barrier probes per 2 MMAs kept the tensor pipe half idle, 0.32 ms -- no gain)
+
+struct P3Smem {
+  uint8_t A[2][P3_WIN_BYTES];
+  uint8_t B[P3_STAGES][P3_B_BYTES];
+  float bias[256];
+  uint64_t a_full[2], a_empty[2], full[P3_STAGES], empty[P3_STAGES], d_full[2], d_empty[2];
+  uint64_t peer_a_full[2], peer_full[P3_STAGES];            // used on the leader: the peer's operands have landed
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+k_conv3_pair_tc(const __half* __restrict__ X3, int64_t a_pitch, const __half* __restrict__ Bp,
+                const float* __restrict__ bias, int64_t M, int n_groups, const float* __restrict__ wd,
+                float* __restrict__ partial, int* __restrict__ err) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  P3Smem& S = *reinterpret_cast<P3Smem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cl = blockIdx.x >> 1, n_cl = gridDim.x >> 1;
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&S.a_full[b], 1); mbar_init(&S.a_empty[b], 1); mbar_init(&S.peer_a_full[b], 1);
+      mbar_init(&S.d_full[b], 1); mbar_init(&S.d_empty[b], 8);        // 4 epilogue warps of each CTA
+    }
+    for (int s = 0; s < P3_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); mbar_init(&S.peer_full[s], 1); }
+    mbar_fence_init();
+  }
+  S.bias[tid] = bias[tid];                 // G_THREADS == 256 output channels
+  if (warp == 2) tmem_alloc_cta2(&S.tmem_base, 512);
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                      // both CTAs' barriers are initialised before anyone signals them
+  fence_after_sync();
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp == 0) {
+    // ---- loader (both CTAs): own window of group g, then own half of the 36 weight slabs
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0, gi = 0;
+      auto load_window = [&](int g, uint32_t k) -> bool {
+        const uint32_t ab = k & 1;
+        if (!mbar_wait(&S.a_empty[ab], ((k >> 1) & 1) ^ 1, kWaitCycles)) return false;
+        mbar_arrive_expect_tx(&S.a_full[ab], P3_WIN_BYTES);
+        const size_t row0 = (size_t)g * 256 + (size_t)rank * P3_ROWS;
+        for (int pl = 0; pl < C3_PLANES; ++pl)
+          bulk_g2s(S.A[ab] + pl * P3_PLANE_BYTES, X3 + ((size_t)pl * a_pitch + row0) * 8, P3_PLANE_BYTES, &S.a_full[ab]);
+        return true;
+      };
+      if (cl < n_groups) { if (!load_window(cl, 0)) { atomicExch(err, 720); goto done; } }
+      for (int g = cl; g < n_groups; g += n_cl, ++gi) {
+        for (int tap = 0; tap < 9; ++tap) {
+          TC_WAIT(&S.empty[s], ph ^ 1, 721);
+          mbar_arrive_expect_tx(&S.full[s], P3_B_BYTES);
+          bulk_g2s(S.B[s], Bp + ((size_t)rank * C3_SLABS + tap * 4) * (P3_B_BYTES / 8), P3_B_BYTES, &S.full[s]);   // w3p: [half][slab][4][128][8]
+          if (++s == P3_STAGES) { s = 0; ph ^= 1; }
+          if (tap == 4 && g + n_cl < n_groups) {
+            if (!load_window(g + n_cl, gi + 1)) { atomicExch(err, 720); goto done; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 1) {
+    // ---- relay (peer CTA): tell the leader when this CTA's window / weight halves have landed
+    if (lane == 0) {
+      uint32_t sg = 0, ph = 0, gi = 0;
+      const uint32_t r_a_full = mapa_shared(smem_u32(&S.peer_a_full[0]), 0), r_full = mapa_shared(smem_u32(&S.peer_full[0]), 0);
+      for (int g = cl; g < n_groups; g += n_cl, ++gi) {
+        const uint32_t ab = gi & 1;
+        TC_WAIT(&S.a_full[ab], (gi >> 1) & 1, 722);
+        mbar_arrive_remote(r_a_full + ab * 8);
+        for (int tap = 0; tap < 9; ++tap) {
+          TC_WAIT(&S.full[sg], ph, 723);
+          mbar_arrive_remote(r_full + sg * 8);
+          if (++sg == P3_STAGES) { sg = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer (leader CTA only)
+    const uint32_t idesc = make_idesc_f16(256, 256);
+    const bool leader = elect_one() != 0;
+    const uint64_t ad0 = make_desc_kmajor_noswizzle(smem_u32(S.A[0]), P3_PLANE_BYTES, 128);
+    const uint64_t bd0 = make_desc_kmajor_noswizzle(smem_u32(S.B[0]), 128 * 16, 128);
+    const uint32_t ad_hi = (uint32_t)(ad0 >> 32), ad_lo = (uint32_t)ad0;
+    const uint32_t bd_hi = (uint32_t)(bd0 >> 32), bd_lo = (uint32_t)bd0;
+    uint32_t sg = 0, ph = 0, gi = 0;
+    for (int g = cl; g < n_groups; g += n_cl, ++gi) {
+      const uint32_t ab = gi & 1, db = gi & 1;
+      TC_WAIT(&S.a_full[ab], (gi >> 1) & 1, 724);
+      TC_WAIT(&S.peer_a_full[ab], (gi >> 1) & 1, 725);
+      TC_WAIT(&S.d_empty[db], ((gi >> 1) & 1) ^ 1, 726);
+      fence_after_sync();
+#pragma unroll 1
+      for (int tap = 0; tap < 9; ++tap) {
+        const uint32_t shift = (tap / 3) * NB + (tap % 3);                // rows
+        TC_WAIT(&S.full[sg], ph, 727);
+        TC_WAIT(&S.peer_full[sg], ph, 728);
+        fence_after_sync();
+        if (leader) {
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {                                // slab = (tap, 32-channel group)
+            const uint32_t b_off = (sg * P3_B_BYTES + gq * (4 * 128 * 16)) >> 4;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(bd_lo + b_off + ((kk * 2 * (128 * 16)) >> 4));
+              const uint64_t ad = ((uint64_t)ad_hi << 32) |
+                                  (uint64_t)(ad_lo + ((ab * P3_WIN_BYTES + (gq * 4 + kk * 2) * P3_PLANE_BYTES + shift * 16) >> 4));
+              mma_ss_cta2(tmem + db * 256, ad, bd, idesc, (tap | gq | kk) != 0);
+            }
+          }
+          commit_cta2(&S.empty[sg]);
+        }
+        __syncwarp();
+        if (++sg == P3_STAGES) { sg = 0; ph ^= 1; }
+      }
+      if (leader) {
+        commit_cta2(&S.d_full[db]);
+        commit_cta2(&S.a_empty[ab]);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ---- epilogue (both CTAs, own 128 rows x all 256 channels): bias + ReLU -> Dense partial sums
+    const int q = warp & 3;
+    uint32_t gi = 0;
+    const uint32_t r_d_empty = mapa_shared(smem_u32(&S.d_empty[0]), 0);
+    for (int g = cl; g < n_groups; g += n_cl, ++gi) {
+      const uint32_t db = gi & 1;
+      TC_WAIT(&S.d_full[db], (gi >> 1) & 1, 729);
+      fence_after_sync();
+      const int64_t r = (int64_t)g * 256 + (int64_t)rank * P3_ROWS + q * 32 + lane;
+      const int rem = (int)(r % PAIR_ROWS);
+      const int yy = rem / NB, xx = rem - yy * NB;
+      const bool valid = (r < M) && (yy < NB - 2) && (xx < NB - 2);
+      // rows are (pair, jb, ib): yy = jb, xx = ib; Flatten order of the reference is (ib, jb, channel)
+      const float* wrow = wd + (size_t)(valid ? (xx * (NB - 2) + yy) : 0) * 256;
+#pragma unroll 1
+      for (int nh = 0; nh < 2; ++nh) {
+        float acc = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + db * 256 + nh * 128 + c0, v);
+          float4 w[8];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) w[j4] = __ldg(reinterpret_cast<const float4*>(wrow + nh * 128 + c0) + j4);
+          tmem_ld_wait();
+          if (nh == 1 && c0 == 96) {          // the last accumulator columns of this group are in registers
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(r_d_empty + db * 8);      // the leader's barrier (also for the leader itself)
+          }
+          const float* bs = S.bias + nh * 128 + c0;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 0]) + bs[j4 * 4 + 0], 0.f), w[j4].x, acc);
+            acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 1]) + bs[j4 * 4 + 1], 0.f), w[j4].y, acc);
+            acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 2]) + bs[j4 * 4 + 2], 0.f), w[j4].z, acc);
+            acc = fmaf(fmaxf(__uint_as_float(v[j4 * 4 + 3]) + bs[j4 * 4 + 3], 0.f), w[j4].w, acc);
+          }
+        }
+        if (r < M) partial[r * 2 + nh] = valid ? acc : 0.f;
+      }
+    }
+  }
+done:
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                      // the leader's MMAs read the peer's shared memory until the very end
+  if (warp == 2) tmem_dealloc_cta2(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_leg_resident_tc -- one leg layer in latency mode (single query scan).
 // Measured (profiles/r1_ncu_summary): the streamed GEMM needs 5 small bulk copies per K slab and a
 // CTA cannot get more than ~1 bulk copy per ~150 clk through, so a 108-slab layer took 45 us at 9 %
@@ -1914,6 +2106,7 @@ int tc_pack_weights(ovn_handle* h) {
   OVN_CUDA(h, cudaFuncSetAttribute(k_delta_conv1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem)));
   OVN_CUDA(h, cudaFuncSetAttribute(k_conv2_sw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(C2Smem)));
   OVN_CUDA(h, cudaFuncSetAttribute(k_conv3_resident_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(C3Smem)));
+  OVN_CUDA(h, cudaFuncSetAttribute(k_conv3_pair_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P3Smem)));
   OVN_CUDA(h, cudaFuncSetAttribute(k_leg_layer1_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   OVN_CUDA(h, cudaFuncSetAttribute(k_leg_layer1_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   OVN_CUDA(h, cudaFuncSetAttribute(k_leg_resident_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LRSmem)));
@@ -2228,8 +2421,22 @@ int heads_forward_tc(ovn_handle* h, const float* d_bank, const float* d_query, c
     prof_mark(h, PROF_CONV2, s);
     OVN_LAUNCH_CHECK(h);
     prof_mark(h, PROF_CONV3, s);
-    k_conv3_resident_tc<<<grid2, G_THREADS, sizeof(C3Smem), s>>>(
-        t->x3, t->rows_pad, t->w3p, t->b3eff, M, n_iter2, h->d_w[base + 3], t->partial, h->d_err);
+    if (getenv("OVN_CONV3_1CTA") != nullptr) {                 // the single-CTA kernel (A/B tests: bit-identical results)
+      k_conv3_resident_tc<<<grid2, G_THREADS, sizeof(C3Smem), s>>>(
+          t->x3, t->rows_pad, t->w3p, t->b3eff, M, n_iter2, h->d_w[base + 3], t->partial, h->d_err);
+    } else {
+      int n_cl = h->sm_count / 2;
+      if (n_cl > n_iter2) n_cl = n_iter2;
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3((unsigned)(2 * n_cl)); lc.blockDim = dim3(G_THREADS); lc.dynamicSmemBytes = sizeof(P3Smem); lc.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      lc.attrs = attr; lc.numAttrs = 1;
+      OVN_CUDA(h, cudaLaunchKernelEx(&lc, k_conv3_pair_tc, (const __half*)t->x3, (int64_t)t->rows_pad, (const __half*)t->w3p,
+                                     (const float*)t->b3eff, (int64_t)M, (int)n_iter2, (const float*)h->d_w[base + 3],
+                                     t->partial, h->d_err));
+    }
     prof_mark(h, PROF_CONV3, s);
     OVN_LAUNCH_CHECK(h);
     k_dense_finalize<<<np, 256, 0, s>>>(t->partial, h->d_b[base + 3], PAIR_ROWS, d_overlap + p0, h->d_err);

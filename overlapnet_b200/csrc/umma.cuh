@@ -206,6 +206,66 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // everything the preceding kernel wrote is visible after this returns
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ---- CTA pairs (tcgen05 cta_group::2): two CTAs of a cluster on one TPC compute one M = 256 tile; each holds
+// its 128 rows of A and HALF of B's N rows at the same shared-memory offsets; the accumulator rows r*128 + lane
+// live in CTA r's tensor memory.  Validated by csrc/cta2_probe.cu (profiles/r2_cta2_probe.txt): SS-mode MMAs run
+// at 0.93-0.96 of the ideal rate (single CTA, N = 128: 0.57), because each CTA fetches only half of B.
+__device__ __forceinline__ void mma_ss_cta2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (when all previously issued MMAs of this thread are complete) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void commit_cta2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// one warp of EACH CTA of the pair executes these (same warp index, same destination offset)
+__device__ __forceinline__ void tmem_alloc_cta2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+               :: "r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cta2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {        // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// arrive on an mbarrier of another CTA of the cluster.  Default (cta-scope) semantics like CUTLASS'
+// umma_arrive_2x1SM_sm0: what the waiter then touches in the peer's shared memory is read by the tensor core
+// (async proxy), and was written by the peer's bulk copies (async proxy) before the peer observed its own
+// barrier; the cluster-scope release / acquire forms cost ~1000 clk per use here (measured: 0.32 -> 0.82 ms).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+// bounded wait with acquire at cluster scope (the arrivals may come from the peer CTA)
+__device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity, long long max_cycles) {
+  const uint32_t a = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return true;
+    if (clock64() - t0 > max_cycles) return false;
+  }
+}
+
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));

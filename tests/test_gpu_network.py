@@ -256,3 +256,29 @@ def test_batched_leg_matches_oracle_and_single_scan_path():
   assert err <= 1e-4
   assert (a - b).abs().max().item() / scale <= 1e-4
   eng.close(); eng1.close()
+
+
+def test_cta_pair_conv3_is_bit_identical_to_single_cta_kernel():
+  """k_conv3_pair_tc (tcgen05 cta_group::2: a CTA pair per 256 x 256 tile, each CTA holding half of the
+  weights) issues the same MMAs in the same order as the single-CTA kernel: identical overlaps."""
+  import os
+  w = N.glorot_weights(4, MODEL, seed=9)
+  bank_np = synth.feature_volumes(12, 41)[:, 0]
+  out = {}
+  for tag in ('pair', 'single'):
+    if tag == 'single':
+      os.environ['OVN_CONV3_1CTA'] = '1'
+    try:
+      eng = Engine(model=MODEL, precision='f16_tc', max_batch_scans=1, max_batch_pairs=64)
+      eng.load_weights(w)
+      bank = torch.from_numpy(bank_np).to(eng.device)
+      ov, yaw, _ = eng.heads_1vsN(bank, bank[3], n_cand=41)          # 41 pairs: a ragged last row group
+      ov1, _, _ = eng.heads_1vsN(bank, bank[3], n_cand=1)            # a single pair (3 row groups)
+      eng.check()
+      out[tag] = (ov.cpu().numpy(), yaw.cpu().numpy(), ov1.cpu().numpy())
+      eng.close()
+    finally:
+      os.environ.pop('OVN_CONV3_1CTA', None)
+  assert np.array_equal(out['pair'][0], out['single'][0]) and np.array_equal(out['pair'][1], out['single'][1])
+  assert np.array_equal(out['pair'][2], out['single'][2]) and out['pair'][2][0] == out['pair'][0][0]
+  assert np.isfinite(out['pair'][0]).all()
