@@ -529,6 +529,9 @@ struct C2Smem {
 // W2 is applied as hi + lo (two MMAs per K16 step and row tile): the kernel streams 1.2 GB of o1 and
 // is HBM-bound, so the second MMA is nearly free, and the fp16 rounding of W2 was the largest single
 // term of the logit error budget after the feature volumes.
+// (Round 2: a CTA-pair version of this kernel -- one row tile and half of the W2 tiles per CTA, cta_group::2 --
+// was built and measured bit-identical but SLOWER, 0.256 vs 0.236 ms: the kernel is bound by the 1.2 GB o1
+// stream from HBM, and the pair's extra barrier hop costs more than the cheaper operand fetch saves.)
 // `fault` != 0 is the test hook of ovn_debug_inject_fault: the loader never arrives, every consumer
 // runs into its bounded barrier wait and the error flag is raised (tests/test_gpu_errors.py).
 __global__ void __launch_bounds__(G_THREADS, 1)

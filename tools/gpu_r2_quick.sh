@@ -3,7 +3,7 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 python -m overlapnet_b200.build > gpurun_out/r2_build.log 2>&1 || cat gpurun_out/r2_build.log | tail -20
-timeout 600 python -m pytest tests/test_gpu_network.py -m gpu -q -x -k "${TESTS:-pair or heads_match or full_size}" > gpurun_out/r2_pytest_quick.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_network.py tests/test_gpu_errors.py -m gpu -q -x -k "${TESTS:-pair or heads_match or full_size or timeout}" > gpurun_out/r2_pytest_quick.log 2>&1
 echo "pytest exit $?"; tail -3 gpurun_out/r2_pytest_quick.log
 timeout 600 python bench.py --steps 20 --warmup 3 --no-extras > gpurun_out/r2_bench_quick.json 2> gpurun_out/r2_bench_quick.err
 echo "bench exit $?"; tail -3 gpurun_out/r2_bench_quick.err
