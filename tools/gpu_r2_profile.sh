@@ -15,7 +15,7 @@ echo "ref exit $?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv \
   python bench.py --steps 2 --warmup 1 --no-extras > gpurun_out/r2_bench_ncu.log 2>&1
 echo "ncu launches exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_delta_conv1_tc|k_conv2_sw_tc|k_conv3_resident_tc|k_corr_tc' -s 10 -c 4 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_delta_conv1_tc|k_conv2_sw_tc|k_conv3_pair_tc|k_corr_tc' -s 10 -c 4 \
   -o gpurun_out/r2_prof_heads python bench.py --steps 1 --warmup 1 --no-extras > gpurun_out/r2_ncu_heads.log 2>&1
 echo "ncu heads exit $?"
 cat > /tmp/one_leg.py <<'PY'
