@@ -346,8 +346,11 @@ def main():
     disc = torch.tensor([int(round(leg_ms / per_pair_ms))], dtype=torch.int32, device=dev)
     if world > 1:
       dist.broadcast(disc, 0)
-    extras = measure_extras(args, eng, w, dev, rank, world, local, timed, q_dev, q_host, cloud_batch, fv_src, bank,
-                            int(disc.item()))
+    try:
+      extras = measure_extras(args, eng, w, dev, rank, world, local, timed, q_dev, q_host, cloud_batch, fv_src, bank,
+                              int(disc.item()))
+    except Exception as e:                                   # the headline line must survive a failing extra
+      extras = {'extras_error': repr(e)[:300]}
 
   if rank == 0:
     pk = peaks()

@@ -45,9 +45,11 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
       objs = list(ex.map(compile_one, srcs))
     subprocess.check_call([nvcc] + NVCC_FLAGS + ['-shared', '-o', LIB] + objs)
-  probe_src = os.path.join(CSRC, 'umma_probe.cu')
-  if os.path.exists(probe_src) and (force or _newer(PROBE, [probe_src] + deps)):
-    subprocess.check_call([nvcc] + NVCC_FLAGS + ['-o', PROBE, probe_src])
+  # standalone known-answer / rate probes of the tcgen05 building blocks (tools, not linked into the library)
+  for name in ('umma_probe', 'cta2_probe'):
+    probe_src, probe_bin = os.path.join(CSRC, name + '.cu'), os.path.join(HERE, name)
+    if os.path.exists(probe_src) and (force or _newer(probe_bin, [probe_src] + deps)):
+      subprocess.check_call([nvcc] + NVCC_FLAGS + ['-o', probe_bin, probe_src])
   return LIB
 
 

@@ -179,3 +179,41 @@ def test_evaluation_flow_matches_reference_semantics(dataset, tmp_path):
     check_yaw(np.array([180 - int(row[3])]), yaw_r, corr_r)
   want = E.error_statistics(m[:, 2], m[:, 3], gt[:, 2], gt[:, 3])
   assert stats == want and stats['yaw_pairs'] == 4
+
+
+def test_infer_four_cue_input_matches_reference_semantics(tmp_path):
+  """BASELINE config 3's input: depth + normal + 20 class probabilities + intensity = 25 channels in the
+  reference's channel order (ImagePairOverlapOrientationSequence.py:143-207), read from the folders the
+  reference's feeder reads (depth/ normal/ probability/ intensity/), through the drop-in Infer."""
+  from overlapnet_b200.infer import Infer
+  root = tmp_path
+  seq = root / '07'
+  for sub in ('depth', 'normal', 'probability', 'intensity'):
+    (seq / sub).mkdir(parents=True)
+  x = synth.range_like_images(17, 3, 25)                          # depth, normal x3, prob x20, intensity
+  for i in range(3):
+    np.save(str(seq / 'depth' / ('%06d.npy' % i)), x[i, :, :, 0])
+    np.save(str(seq / 'normal' / ('%06d.npy' % i)), x[i, :, :, 1:4])
+    np.save(str(seq / 'probability' / ('%06d.npy' % i)), x[i, :, :, 4:24])
+    np.save(str(seq / 'intensity' / ('%06d.npy' % i)), x[i, :, :, 24])
+  w = N.glorot_weights(25, MODEL, seed=4)
+  fvs = N.leg_forward(x, w, MODEL)
+  li, ri = np.array([1, 0, 2, 1]), np.array([0, 2, 1, 2])
+  _, _, _, z0 = N.heads_forward(fvs[li], fvs[ri], w, MODEL, return_logit=True)
+  w = N.spread_dense(w, z0, target_std=1.5)
+  wpath = str(root / 'w.npz')
+  W.save_npz(wpath, w)
+  cfg = {'pretrained_weightsfilename': wpath, 'use_depth': True, 'use_normals': True, 'use_class_probabilities': True,
+         'use_class_probabilities_pca': False, 'use_intensity': True, 'data_root_folder': str(root),
+         'infer_seqs': '07', 'batch_size': 16, 'model': copy.deepcopy(MODEL)}
+  inf = Infer(copy.deepcopy(cfg), precision='f16_tc')
+  ref = InferRef(copy.deepcopy(cfg), w)
+  assert inf.no_input_channels == 25 and inf.inputShape == [64, 900, 25]
+  names = ['000000', '000001', '000002']
+  fv = inf.create_feature_volumes(names)
+  fv_r = ref.create_feature_volumes(names)
+  assert np.abs(fv - fv_r).max() / np.abs(fv_r).max() <= 1e-4
+  got = inf.infer_multiple_vs_multiple(names, [0, 2, 1, 2], [1, 0, 2, 1])     # LEFT = second_idxs, RIGHT = first_idxs
+  want = ref.infer_multiple_vs_multiple(names, [0, 2, 1, 2], [1, 0, 2, 1])
+  assert np.abs(got[0] - want[0]).max() <= 1e-3
+  check_yaw(got[1], want[1], want[2])
