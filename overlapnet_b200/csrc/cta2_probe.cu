@@ -14,38 +14,12 @@
 #include "umma.cuh"
 using namespace umma;
 
-__device__ __forceinline__ void mma_ss_cta2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-      :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
 __device__ __forceinline__ void mma_ts_cta2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
       :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void commit_cta2(uint64_t* bar) {         // arrives on the barrier at this offset in BOTH CTAs
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_cta2(uint32_t* dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(dst)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_cta2(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 // A: [256][K] row-major, B: [N][K] row-major (D = A B^T), D: [256][N] fp32.  mode 0 = known answer, 1 = rate.
 __global__ void __launch_bounds__(128, 1)
 probe(const __half* __restrict__ gA, const __half* __restrict__ gB, float* __restrict__ gD, int N, int K, int mode,
@@ -54,7 +28,7 @@ probe(const __half* __restrict__ gA, const __half* __restrict__ gB, float* __res
   __shared__ uint64_t bar;
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = cluster_rank();
+  const uint32_t rank = cluster_ctarank();
   const int Nh = N / 2;                                   // B rows held by each CTA
   __half* sA = reinterpret_cast<__half*>(smem);           // [K/8][128][8]
   __half* sB = reinterpret_cast<__half*>(smem + 64 * 1024);   // [K/8][Nh][8]
