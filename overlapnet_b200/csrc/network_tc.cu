@@ -136,12 +136,23 @@ k_channel_mean(const float* __restrict__ bank, const int32_t* __restrict__ idx, 
 constexpr int K4_GROUPS = OVN_K4_GROUPS; // producer groups of 4 warps (one per TMEM lane quarter); group g owns steps with step % K4_GROUPS == g
 constexpr int K4_PROD_WARPS = 4 * K4_GROUPS;
 constexpr int K4_THREADS = (8 + K4_PROD_WARPS) * 32;
-constexpr int K4_STAGES = 6;            // A ring: TMEM column slots
+#ifndef OVN_K4_ROT
+#define OVN_K4_ROT 0
+#endif
+// OVN_K4_ROT = 1 (round-2 experiment, correct but SLOWER, kept as a build switch): FOUR accumulator tiles used
+// round-robin by the three row tiles of consecutive units (unit u, tile t -> physical tile (3u + t) mod 4), paid for
+// with one A ring slot (5 x 48 columns instead of 6).  The first tile of the next unit is then always free and the
+// second is the one the epilogue pulled first, which removes the issuer's ~1000 clk wait per unit for the
+// single-buffered accumulators -- but the shallower A ring costs more in steady state: measured on one box,
+// back to back, 2.06-2.08 ms against 1.91-1.98 ms (tools/gpu_r2_ab.sh, profiles/r2_k4_rot_ab.txt).
+constexpr int K4_DTILES = OVN_K4_ROT ? 4 : 3;
+constexpr int K4_STAGES = OVN_K4_ROT ? 5 : 6;   // A ring: TMEM column slots
 constexpr int K4_BGROUPS = 3;           // B ring: 3 groups of 6 consecutive W1 slices (24 KB, one bulk copy, one barrier each;
                                         //   4 groups measured no faster, and the 24 KB pay for the epilogue staging)
-constexpr int K4_BSLOTS = K4_BGROUPS * 6;
+constexpr int K4_BSLOTS = K4_BGROUPS * K4_STAGES;
 constexpr int K4_TILES = 3;
-constexpr int K4_ACOL0 = 192;           // TMEM columns: D = [0,192), A stages = [192, 192 + 6*48)
+constexpr int K4_ACOL0 = K4_DTILES * 64; // TMEM columns: D = [0, 64 * K4_DTILES), A stages behind it (48 columns each)
+static_assert(K4_DTILES * 64 + K4_STAGES * 48 <= 512 && 60 % K4_STAGES == 0 && (60 / K4_STAGES) % 2 == 0, "k_delta_conv1_tc TMEM / ring layout");
 constexpr int K4_STAGE_COLS = 48;
 constexpr int K4_STEPS = 60;            // 4 channel chunks x 15 dj per jb
 constexpr int K4_BSLICE = 4096;         // bytes of W1 per step: [4 k8][64 o][8]
@@ -162,7 +173,7 @@ struct K4Smem {
   __half B[K4_BSLOTS][K4_BSLICE / 2];
   uint8_t epi[K4_TILES][4][32 * 128];   // [tile][epilogue warp]: 32 fp16 output rows staged for the transposed store
   uint64_t a_full[K4_STAGES], a_empty[K4_STAGES], b_full[K4_BGROUPS], b_empty[K4_BGROUPS];
-  uint64_t d_full, d_empty[K4_TILES], l_full, l_empty, rw_full[2], rw_empty[2];
+  uint64_t d_full, d_empty[K4_DTILES], l_full, l_empty, rw_full[2], rw_empty[2];
   float mu_o1[64];                      // per-channel centre subtracted before the fp16 rounding of o1
   uint32_t tmem_base;
 };
@@ -211,7 +222,7 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_i
     for (int s = 0; s < K4_STAGES; ++s) { mbar_init(&S.a_full[s], 4); mbar_init(&S.a_empty[s], 1); }
     for (int s = 0; s < K4_BGROUPS; ++s) { mbar_init(&S.b_full[s], 1); mbar_init(&S.b_empty[s], 1); }
     mbar_init(&S.d_full, 1);
-    for (int t = 0; t < K4_TILES; ++t) mbar_init(&S.d_empty[t], 4);
+    for (int t = 0; t < K4_DTILES; ++t) mbar_init(&S.d_empty[t], 4);
     mbar_init(&S.l_full, 1); mbar_init(&S.l_empty, K4_PROD_WARPS);
     for (int b = 0; b < 2; ++b) { mbar_init(&S.rw_full[b], 1); mbar_init(&S.rw_empty[b], K4_PROD_WARPS); }
     mbar_fence_init();
@@ -273,8 +284,13 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_i
       // probe latency hides behind the MMAs being issued; only a failed probe falls back to a wait.
       const uint32_t a_full0 = smem_u32(&S.a_full[0]), b_full0 = smem_u32(&S.b_full[0]);
       uint32_t ui = 0, bg = 0, bph = 0;
+      uint32_t dcnt[K4_DTILES] = {};        // how often each physical accumulator tile has been handed to a unit so far
       bool ready = false, bready = false;
       for (int u = u_begin; u < u_end; ++u, ++ui) {
+        // physical accumulator tile of this unit's row tile t
+        uint32_t pt[K4_TILES];
+#pragma unroll
+        for (int t = 0; t < K4_TILES; ++t) pt[t] = OVN_K4_ROT ? ((3u * ui + t) & 3u) : (uint32_t)t;
 #pragma unroll 1
         for (uint32_t o = 0; o < K4_STEPS / K4_STAGES; ++o) {
           const uint32_t ph = o & 1;            // (step / 6) & 1: 10 groups per unit
@@ -297,14 +313,22 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_i
               // each tile as soon as the epilogue has pulled that tile of the previous unit into
               // registers.  (Running the first six steps tile-major was measured slower: the producers
               // have only just been given the six slots back and tile 0 then waits for slot 5.)
+#pragma unroll
               for (int t = 0; t < K4_TILES; ++t) {
-                TC_WAIT(&S.d_empty[t], (ui & 1) ^ 1, 201);
+                // the epilogue has pulled the previous contents of this physical tile (its k-th release, k = dcnt - 1)
+#pragma unroll
+                for (int p = 0; p < K4_DTILES; ++p) {
+                  if (pt[t] == (uint32_t)p) {
+                    TC_WAIT(&S.d_empty[p], (dcnt[p] & 1) ^ 1, 201);
+                    ++dcnt[p];
+                  }
+                }
                 fence_after_sync();
                 if (leader) {
 #pragma unroll
                   for (int kk = 0; kk < 2; ++kk) {
                     const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_lo + ((kk * 2048) >> 4));
-                    mma_ts(tmem + t * 64, tmem + K4_ACOL0 + t * 16 + kk * 8, bd, idesc, kk != 0);
+                    mma_ts(tmem + pt[t] * 64, tmem + K4_ACOL0 + t * 16 + kk * 8, bd, idesc, kk != 0);
                   }
                 }
                 __syncwarp();
@@ -321,7 +345,7 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_i
                 const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_lo + ((sg * K4_BSLICE + kk * 2048) >> 4));
 #pragma unroll
                 for (int t = 0; t < K4_TILES; ++t) {
-                  mma_ts(tmem + t * 64, tmem + K4_ACOL0 + sg * K4_STAGE_COLS + t * 16 + kk * 8, bd, idesc, 1);
+                  mma_ts(tmem + pt[t] * 64, tmem + K4_ACOL0 + sg * K4_STAGE_COLS + t * 16 + kk * 8, bd, idesc, 1);
                 }
               }
               commit(&S.a_empty[sg]);
@@ -358,13 +382,14 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_i
 #pragma unroll 1
       for (int t = 0; t < K4_TILES; ++t) {
         uint32_t v0[32], v1[32];
+        const uint32_t ptile = OVN_K4_ROT ? ((3u * ui + (uint32_t)t) & 3u) : (uint32_t)t;   // physical accumulator tile
         K4_TR(q == 0 && lane == 0 && u == u_begin + 1, 4, 1 + t, 1, clock64());
-        tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + t * 64, v0);
-        tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + t * 64 + 32, v1);
+        tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + ptile * 64, v0);
+        tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + ptile * 64 + 32, v1);
         tmem_ld_wait();
         fence_before_sync();                 // this tile is in registers: hand it back to the MMA issuer
         __syncwarp();
-        if (lane == 0) mbar_arrive(&S.d_empty[t]);
+        if (lane == 0) mbar_arrive(&S.d_empty[ptile]);
         K4_TR(q == 0 && lane == 0 && u == u_begin + 1, 4, 1 + t, 0, clock64());
         // (the c_conv1 bias is folded into the c_conv2 bias at pack time: both layers are linear)
         uint8_t* row = S.epi[t][q] + lane * 128;
