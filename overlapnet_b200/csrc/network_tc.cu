@@ -171,14 +171,16 @@ struct K4Smem {
   __half L[WF * K4_PITCH];
   __half Rw[2][S15 * K4_PITCH];         // double-buffered RIGHT-row window (streamed per jb)
   __half B[K4_BSLOTS][K4_BSLICE / 2];
+  __half Bc[2 * 64 * 8];                // constant K16 x N64 B slice: row k = 0 holds -mu_o1[o], the rest is zero
   uint8_t epi[K4_TILES][4][32 * 128];   // [tile][epilogue warp]: 32 fp16 output rows staged for the transposed store
   uint64_t a_full[K4_STAGES], a_empty[K4_STAGES], b_full[K4_BGROUPS], b_empty[K4_BGROUPS];
   uint64_t d_full, d_empty[K4_DTILES], l_full, l_empty, rw_full[2], rw_empty[2];
-  float mu_o1[64];                      // per-channel centre subtracted before the fp16 rounding of o1
   uint32_t tmem_base;
 };
 
 static_assert(sizeof(K4Smem) <= 232448, "k_delta_conv1_tc shared memory");
+constexpr int K4_ONES_COL = K4_ACOL0 + K4_STAGES * K4_STAGE_COLS;     // 8 TMEM columns: A operand "1 at k = 0"
+static_assert(K4_ONES_COL + 8 <= 512, "k_delta_conv1_tc TMEM layout");
 
 // Development aid (tools/k4_trace.py): a build with -DOVN_K4_TRACE records clock64() timestamps of
 // CTA 0's roles for one jb.  Compiled out of the product library.
@@ -228,11 +230,31 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_i
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(&S.tmem_base, 512);
-  if (tid >= 64 && tid < 128) S.mu_o1[tid - 64] = mu_o1[tid - 64];
+  // The o1 centre is subtracted BY THE TENSOR CORE: the first MMA of every accumulator tile of a unit is
+  // D = ones(k = 0) x Bc with Bc[0][o] = -mu_o1[o] (fp16; k_o1_channel_mean rounds mu_o1 to fp16 so that the
+  // bias fold downstream uses exactly the subtracted value).  Doing it in the epilogue (64 FADD + 16 LDS per
+  // row tile in front of the next tile's tcgen05.ld) cost 3 % of this kernel (profiles/r2_k4_center_ab.txt).
+  if (tid >= 64 && tid < 128) {
+    const int o = tid - 64;
+    const __half neg = __float2half_rn(-mu_o1[o]);
+    uint4 z = make_uint4(0u, 0u, 0u, 0u), f = z;
+    f.x = (uint32_t)__half_as_ushort(neg);
+    *reinterpret_cast<uint4*>(&S.Bc[(0 * 64 + o) * 8]) = f;        // k = 0..7 of channel o
+    *reinterpret_cast<uint4*>(&S.Bc[(1 * 64 + o) * 8]) = z;        // k = 8..15
+  }
+  fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = S.tmem_base;
+  if (warp >= 4 && warp < 8) {             // the constant A operand: every lane (row) holds 1.0 at k = 0
+    const uint32_t ones[8] = {0x00003c00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    tmem_st_x8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + K4_ONES_COL, ones);
+    tmem_st_wait();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
   constexpr uint32_t VOL_BYTES = WF * K4_PITCH * 2;
 
   if (warp == 0) {
@@ -276,6 +298,7 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_i
     {
       const uint32_t idesc = make_idesc_f16(128, 64);
       const uint64_t bdesc0 = make_desc_kmajor_noswizzle(smem_u32(S.B[0]), 1024, 128);
+      const uint64_t bdesc_c = make_desc_kmajor_noswizzle(smem_u32(S.Bc), 1024, 128);
       const uint32_t bd_hi = (uint32_t)(bdesc0 >> 32), bd_lo = (uint32_t)bdesc0;
       const bool leader = elect_one() != 0;
       // An mbarrier probe costs ~90 clk even when the phase is already complete, and this warp is the
@@ -325,10 +348,11 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_i
                 }
                 fence_after_sync();
                 if (leader) {
+                  mma_ts(tmem + pt[t] * 64, tmem + K4_ONES_COL, bdesc_c, idesc, 0);          // D = -mu_o1 (overwrites)
 #pragma unroll
                   for (int kk = 0; kk < 2; ++kk) {
                     const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_lo + ((kk * 2048) >> 4));
-                    mma_ts(tmem + pt[t] * 64, tmem + K4_ACOL0 + t * 16 + kk * 8, bd, idesc, kk != 0);
+                    mma_ts(tmem + pt[t] * 64, tmem + K4_ACOL0 + t * 16 + kk * 8, bd, idesc, 1);
                   }
                 }
                 __syncwarp();
@@ -402,8 +426,7 @@ k_delta_conv1_tc(const __half* __restrict__ L16, const int32_t* __restrict__ l_i
             for (int j = 0; j < 4; ++j) {
               const uint32_t a = c ? v1[h8 * 8 + 2 * j] : v0[h8 * 8 + 2 * j];
               const uint32_t b = c ? v1[h8 * 8 + 2 * j + 1] : v0[h8 * 8 + 2 * j + 1];
-              const float2 m = *reinterpret_cast<const float2*>(&S.mu_o1[c * 32 + h8 * 8 + 2 * j]);   // broadcast LDS
-              __half2 hh = __floats2half2_rn(__uint_as_float(a) - m.x, __uint_as_float(b) - m.y);
+              __half2 hh = __floats2half2_rn(__uint_as_float(a), __uint_as_float(b));   // (the centre is already subtracted)
               pk[j] = *reinterpret_cast<uint32_t*>(&hh);
             }
             *reinterpret_cast<uint4*>(row + (((c * 4 + h8) ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -1752,7 +1775,7 @@ k_o1_channel_mean(const __half* __restrict__ o1, int64_t M, float* __restrict__ 
   if (g == 0) {
     float t = 0.f;
     for (int k = 0; k < 16; ++k) t += part[k][o];
-    mu[o] = t / (float)(M * S15);
+    mu[o] = __half2float(__float2half_rn(t / (float)(M * S15)));   // fp16: k_delta_conv1_tc subtracts it as an MMA operand
   }
 }
 
