@@ -191,6 +191,13 @@ def test_infer_four_cue_input_matches_reference_semantics(tmp_path):
   for sub in ('depth', 'normal', 'probability', 'intensity'):
     (seq / sub).mkdir(parents=True)
   x = synth.range_like_images(17, 3, 25)                          # depth, normal x3, prob x20, intensity
+  # three scans of DIFFERENT statistics (nearer / farther scene, other class mix, darker returns): three iid-noise
+  # images give near-identical volumes, a logit std of 0.0018 and an 850x amplification at spread 1.5 -- a
+  # numerical-analysis stress case (tools/precision_study.py), not a scan pair
+  x[1, ..., 0] *= 0.4
+  x[2, ..., 0] *= 1.8
+  x[1, ..., 4:24] = np.roll(x[1, ..., 4:24], 5, axis=-1) * 0.5
+  x[2, ..., 24] *= 0.2
   for i in range(3):
     np.save(str(seq / 'depth' / ('%06d.npy' % i)), x[i, :, :, 0])
     np.save(str(seq / 'normal' / ('%06d.npy' % i)), x[i, :, :, 1:4])
