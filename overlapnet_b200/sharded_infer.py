@@ -9,7 +9,6 @@ reference frames it owns and ONE gather returns the 8-byte (overlap, yaw) record
 With world size 1 (or no process group) it behaves exactly like ``Infer``.
 """
 import numpy as np
-import torch
 
 from .engine import FEAT_C
 from .infer import Infer

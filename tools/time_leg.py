@@ -3,7 +3,7 @@
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import numpy as np, torch
+import torch
 from overlapnet_b200 import synth
 from overlapnet_b200.engine import Engine
 sys.path.insert(0, ROOT)
