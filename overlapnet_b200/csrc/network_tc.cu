@@ -51,6 +51,11 @@ struct TcState {
   // tensor-core leg (layers 2..): packed weights + copy tables per layer, ping-pong activation planes
   __half* wres[kMaxLegLayers] = {};      // [cout/64][kh*kw*3][C_in/8][64][8] (resident-activation kernels)
   __half* actp[2] = {nullptr, nullptr};
+  // layer 1 on tensor cores (batched encode): the stride-2 columns are de-interleaved into even / odd planes, which
+  // turns the 5 x 15 stride-(2,2) conv over C channels into a 5 x 8 stride-(2,1) conv over 2C channels
+  __half* in_planes = nullptr;          // [max_batch_scans][H][hi,lo][l1_c8in][ceil(W/2)][8]
+  int l1_c8in = 0;                      // (2C rounded up to a multiple of 16) / 8
+  bool l1_tc = false;
   float* leg_part = nullptr;     // split-K partial tiles of the latency-mode leg: [kLegPartTiles][128 x 64] fp32
   int* leg_counters = nullptr;   // [kLegPartTiles * 4] arrival counters (always left at zero)
   __half* l16 = nullptr;        // [max_pairs][360][128]
@@ -1304,19 +1309,25 @@ done:
 // ------------------------------------------------------------------------------------------------
 constexpr int LB_A_MAX = 139264;                  // 2 x 2 x 8 planes x 272 px x 16 B (s_conv4 with two tiles)
 
-struct LBSmem {
-  uint8_t A[LB_A_MAX];
-  uint8_t B[LR_STAGES][LR_B_MAX];
+constexpr int LB_A_FAT = 188416;                  // layer 1 with 25 input channels: 5 x 2 x 8 planes x 144 px x 16 B (+ slack)
+
+template <int STAGES, int A_MAX>
+struct LBSmemT {
+  uint8_t A[A_MAX];
+  uint8_t B[STAGES][LR_B_MAX];
   float bias[64];
-  uint64_t a_full, full[LR_STAGES], empty[LR_STAGES], d_full;
+  uint64_t a_full, full[STAGES], empty[STAGES], d_full;
   uint32_t tmem_base;
 };
+using LBSmem = LBSmemT<LR_STAGES, LB_A_MAX>;
+using LBSmemFat = LBSmemT<2, LB_A_FAT>;          // a fat window leaves room for a 2-stage weight ring only
 
-template <int EPI, int TILES>
+template <int EPI, int TILES, int STAGES = LR_STAGES, int A_MAX = LB_A_MAX>
 __global__ void __launch_bounds__(G_THREADS, 1)
 k_leg_batched_tc(LegArgs g, int n_mma, int* __restrict__ err) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  LBSmem& S = *reinterpret_cast<LBSmem*>(smem_raw);
+  using Smem = LBSmemT<STAGES, A_MAX>;
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   constexpr int WIN = TILES * 128 + 16;             // pixels per window plane (kw <= 15)
   constexpr uint32_t TMEM_COLS = TILES * 64;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1332,7 +1343,7 @@ k_leg_batched_tc(LegArgs g, int n_mma, int* __restrict__ err) {
 
   if (tid == 0) {
     mbar_init(&S.a_full, 1);
-    for (int s = 0; s < LR_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
     mbar_init(&S.d_full, 1);
     mbar_fence_init();
   }
@@ -1357,7 +1368,7 @@ k_leg_batched_tc(LegArgs g, int n_mma, int* __restrict__ err) {
         bulk_g2s(S.B[s], g.Bp + ((size_t)nh * n_slabs + sl) * (b_bytes / 2), (uint32_t)cnt * b_bytes, &S.full[s]);
       }
       __syncwarp();
-      if (++s == LR_STAGES) { s = 0; ph ^= 1; }
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_f16(128, n_mma);
@@ -1397,7 +1408,7 @@ k_leg_batched_tc(LegArgs g, int n_mma, int* __restrict__ err) {
       }
       if (leader) commit(&S.empty[sg]);
       __syncwarp();
-      if (++sg == LR_STAGES) { sg = 0; ph ^= 1; }
+      if (++sg == STAGES) { sg = 0; ph ^= 1; }
     }
     if (leader) commit(&S.d_full);
     __syncwarp();
@@ -1989,6 +2000,33 @@ k_leg_layer1_small(const float* __restrict__ x, const float* __restrict__ w, con
   *reinterpret_cast<uint4*>(out + ((size_t)(plane_hi + C8) * W_out + xo) * 8) = *reinterpret_cast<const uint4*>(lo);
 }
 
+// fp32 NHWC [n][H][W][C] -> hi/lo fp16 planes [n][H][hi,lo][c8in][ceil(W/2)][8] with channel' = parity * C + c
+// (parity = column & 1): the input of the tensor-core layer 1 (see TcState::in_planes)
+__global__ void __launch_bounds__(256)
+k_input_to_parity_planes(const float* __restrict__ x, int64_t total, int H, int W, int C, int c8in, int Wh,
+                         __half* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // (img*H + h, c8, w')
+  if (i >= total) return;
+  const int wp = (int)(i % Wh);
+  int64_t r = i / Wh;
+  const int c8 = (int)(r % c8in); r /= c8in;                               // r = img*H + h
+  __half hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int ch = c8 * 8 + e;
+    float v = 0.f;
+    if (ch < 2 * C) {
+      const int parity = ch / C, c = ch - parity * C, w = 2 * wp + parity;
+      if (w < W) v = __ldg(x + (r * W + w) * (int64_t)C + c);
+    }
+    hi[e] = __float2half_rn(v);
+    lo[e] = __float2half_rn(v - __half2float(hi[e]));
+  }
+  const int64_t plane_hi = r * (2 * c8in) + c8;
+  *reinterpret_cast<uint4*>(out + ((size_t)plane_hi * Wh + wp) * 8) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(out + ((size_t)(plane_hi + c8in) * Wh + wp) * 8) = *reinterpret_cast<const uint4*>(lo);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -2010,6 +2048,7 @@ void tc_free(ovn_handle* h) {
   if (t->pb_lc) cudaFree(t->pb_lc);
   if (t->leg_part) cudaFree(t->leg_part);
   if (t->leg_counters) cudaFree(t->leg_counters);
+  if (t->in_planes) cudaFree(t->in_planes);
   if (t->actp[0]) cudaFree(t->actp[0]);
   if (t->actp[1]) cudaFree(t->actp[1]);
   delete t;
@@ -2129,6 +2168,44 @@ int tc_pack_weights(ovn_handle* h) {
       if ((rc2 = upload_vec(h, &t->wres[l], br)) != OVN_OK) return rc2;
     }
   }
+  {
+    // ---- layer 1 on tensor cores: W'[dh][j][parity*C + c][n] = W[dh][2j + parity][c][n]  (kw' = ceil(kw / 2))
+    const ConvSpec& L = h->leg[0];
+    const int c8in = (((2 * L.cin + 7) / 8) + 1) & ~1;
+    const int kwp = (L.kw + 1) / 2;
+    // measured (batch 64, us/scan, whole leg): C = 25: 52.4 direct -> 41.8 here; C = 4: 16.4 direct -> 20.9 here
+    // (N = 16 MMAs are bound by the shared-memory read of A), so only wide inputs take this path
+    t->l1_tc = L.cin > 8 && L.sw == 2 && L.cout == 16 && kwp <= 16 &&
+               (size_t)L.kh * 2 * c8in * (128 + 16) * 16 <= (size_t)LB_A_FAT && (size_t)c8in * 64 * 16 <= (size_t)LR_B_MAX;
+    if (t->l1_tc) {
+      const LayerWeights& w = h->host_w[L.name];
+      const int nsl = L.kh * kwp * 3;
+      std::vector<__half> br((size_t)nsl * c8in * 64 * 8, __float2half(0.f));
+      for (int dh = 0; dh < L.kh; ++dh)
+        for (int j = 0; j < kwp; ++j)
+          for (int term = 0; term < 3; ++term) {
+            const int sl = (dh * kwp + j) * 3 + term;
+            for (int c8 = 0; c8 < c8in; ++c8)
+              for (int n = 0; n < L.cout; ++n)
+                for (int k = 0; k < 8; ++k) {
+                  const int ch = c8 * 8 + k;
+                  if (ch >= 2 * L.cin) continue;
+                  const int parity = ch / L.cin, c = ch - parity * L.cin, dw = 2 * j + parity;
+                  if (dw >= L.kw) continue;
+                  const float wf = w.kernel[(((size_t)dh * L.kw + dw) * L.cin + c) * L.cout + n];
+                  const __half wh = __float2half(wf);
+                  const __half wl = __float2half(wf - __half2float(wh));
+                  br[(((size_t)sl * c8in + c8) * 64 + n) * 8 + k] = (term == 2) ? wl : wh;
+                }
+          }
+      int rc2;
+      if ((rc2 = upload_vec(h, &t->wres[0], br)) != OVN_OK) return rc2;
+      t->l1_c8in = c8in;
+      const size_t bytes = (size_t)h->cfg.max_batch_scans * L.h_in * 2 * c8in * ((L.w_in + 1) / 2) * 16 + 32768;
+      OVN_CUDA(h, cudaMalloc(&t->in_planes, bytes));
+      OVN_CUDA(h, cudaMemset(t->in_planes, 0, bytes));
+    }
+  }
   for (int b = 0; b < 2; ++b) {
     const size_t bytes = max_planes_bytes * h->cfg.max_batch_scans + 32768;   // + tile overrun slack
     OVN_CUDA(h, cudaMalloc(&t->actp[b], bytes));
@@ -2165,6 +2242,7 @@ int tc_pack_weights(ovn_handle* h) {
 #define OVN_LB_ATTR(E, T) OVN_CUDA(h, cudaFuncSetAttribute(k_leg_batched_tc<E, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LBSmem)))
   OVN_LB_ATTR(3, 1); OVN_LB_ATTR(3, 2); OVN_LB_ATTR(3, 4); OVN_LB_ATTR(4, 1); OVN_LB_ATTR(4, 2); OVN_LB_ATTR(4, 4);
 #undef OVN_LB_ATTR
+  OVN_CUDA(h, cudaFuncSetAttribute(k_leg_batched_tc<4, 1, 2, LB_A_FAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LBSmemFat)));
   return OVN_OK;
 }
 
@@ -2203,7 +2281,30 @@ int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cuda
     const int64_t chunks = (int64_t)n * L.h_out * (L.cout / 8) * L.w_out;
     const size_t w_bytes = (size_t)L.kw * L.cin * L.cout * sizeof(float);        // one kernel row of taps
     const size_t w_all = w_bytes * L.kh;
-    if (n <= 2 && w_all <= 200 * 1024 && L.cout % 8 == 0) {
+    if (n > 2 && t->l1_tc) {
+      // batched encode: layer 1 on tensor cores through even / odd column planes
+      const int c8in = t->l1_c8in, Wh = (L.w_in + 1) / 2, kwp = (L.kw + 1) / 2;
+      const int64_t total = (int64_t)n * L.h_in * c8in * Wh;
+      k_input_to_parity_planes<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_input, total, L.h_in, L.w_in, L.cin, c8in, Wh,
+                                                                           t->in_planes);
+      OVN_LAUNCH_CHECK(h);
+      LegArgs la = {};
+      la.A = t->in_planes; la.a_pitch = Wh; la.runs_per_img = L.h_out; la.in_img_planes = L.h_in * 2 * c8in;
+      la.in_run_planes = L.sh * 2 * c8in; la.kh = L.kh; la.kw = kwp; la.c8in = c8in; la.Bp = t->wres[0];
+      la.bias = h->d_b[0]; la.n_valid = L.cout; la.M = L.w_out; la.out_planes = t->actp[0]; la.out_pitch = L.w_out;
+      la.out_run_planes = 2 * (L.cout / 8); la.out_f32 = nullptr; la.n_split = 1;
+      const size_t win2 = (size_t)L.kh * 2 * c8in * (2 * 128 + 16) * 16, win1 = (size_t)L.kh * 2 * c8in * (128 + 16) * 16;
+      if (win2 <= (size_t)LB_A_MAX) {
+        const dim3 grid((unsigned)((L.w_out + 255) / 256), (unsigned)(n * L.h_out), 1);
+        k_leg_batched_tc<4, 2><<<grid, G_THREADS, sizeof(LBSmem), s>>>(la, 16, h->d_err);
+      } else if (win1 <= (size_t)LB_A_MAX) {
+        const dim3 grid((unsigned)((L.w_out + 127) / 128), (unsigned)(n * L.h_out), 1);
+        k_leg_batched_tc<4, 1><<<grid, G_THREADS, sizeof(LBSmem), s>>>(la, 16, h->d_err);
+      } else {
+        const dim3 grid((unsigned)((L.w_out + 127) / 128), (unsigned)(n * L.h_out), 1);
+        k_leg_batched_tc<4, 1, 2, LB_A_FAT><<<grid, G_THREADS, sizeof(LBSmemFat), s>>>(la, 16, h->d_err);
+      }
+    } else if (n <= 2 && w_all <= 200 * 1024 && L.cout % 8 == 0) {
       const unsigned grid = (unsigned)((chunks + 255) / 256);
       if (L.cin == 4)
         k_leg_layer1_small<true><<<grid, 256, w_all, s>>>(d_input, h->d_w[0], h->d_b[0], n, L.h_in, L.w_in, L.cin, L.kh, L.kw,

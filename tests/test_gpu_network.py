@@ -134,6 +134,30 @@ def test_leg_other_channel_counts(channels, use):
     eng.close()
 
 
+@pytest.mark.parametrize('channels,use', [(5, {'use_intensity': True}),
+                                          (25, {'use_intensity': True, 'use_class_probabilities': True})])
+def test_batched_leg_other_channel_counts(channels, use):
+  """Batches of more than two scans take layer 1 on tensor cores (even / odd column planes, 2C channels
+  zero-padded to a multiple of 16; C = 25 needs the fat-window instantiation): fp32-grade against the
+  float64 oracle, and the same volumes as the one-scan-at-a-time path."""
+  w = N.glorot_weights(channels, MODEL, seed=3)
+  x = synth.range_like_images(9, 5, channels)
+  ref = N.leg_forward(x, w, MODEL)[:, 0]
+  scale = np.abs(ref).max()
+  eng = Engine(use=use, model=MODEL, precision='f16_tc', max_batch_scans=5, max_batch_pairs=1)
+  eng1 = Engine(use=use, model=MODEL, precision='f16_tc', max_batch_scans=1, max_batch_pairs=1)
+  eng.load_weights(w); eng1.load_weights(w)
+  xt = torch.from_numpy(x).to(eng.device)
+  a = eng.leg(xt)
+  assert torch.equal(eng.leg(xt), a)
+  err = np.abs(a.cpu().numpy() - ref).max() / scale
+  print('\n[parity] batched leg C=%d (tensor-core layer 1): max rel err vs float64 oracle = %.3e' % (channels, err))
+  assert err <= 1e-4
+  assert (a - eng1.leg(xt)).abs().max().item() / scale <= 1e-4
+  eng.check()
+  eng.close(); eng1.close()
+
+
 def test_full_size_1xN_properties():
   """BASELINE config 2 size (1 query x 1101 candidates) through the product path: results are
   independent of candidate order / chunking, equal to the pairwise entry point, the query
