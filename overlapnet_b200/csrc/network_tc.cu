@@ -49,7 +49,11 @@ struct TcState {
   __half* w3p = nullptr;        // [2 halves][36 slabs][4][128][8]
   float* b2eff = nullptr;       // c_conv2 bias + the c_conv1 bias pushed through W2 (both layers are linear)
   // tensor-core leg (layers 2..): packed weights + copy tables per layer, ping-pong activation planes
-  __half* wres[kMaxLegLayers] = {};      // [cout/64][kh*kw*3][C_in/8][64][8] (resident-activation kernels)
+  __half* wres[kMaxLegLayers] = {};      // [cout/64][kh*kw*3][C_in/8][64][8] (latency-mode kernel)
+  // batched kernel: per tap the hi and lo halves of the weights stacked along N, [cout/64][kh*kw][C_in/8/c8u][c8u][2 n_mma][8]
+  // with rows [0, n_mma) = hi, [n_mma, 2 n_mma) = lo: x*w ~= xh*[wh; wl] (one MMA, N = 2 n_mma) + xl*wh (N = n_mma)
+  __half* wstk[kMaxLegLayers] = {};
+  int stk_c8u[kMaxLegLayers] = {};
   __half* actp[2] = {nullptr, nullptr};
   // layer 1 on tensor cores (batched encode): the stride-2 columns are de-interleaved into even / odd planes, which
   // turns the 5 x 15 stride-(2,2) conv over C channels into a 5 x 8 stride-(2,1) conv over 2C channels
@@ -1089,7 +1093,8 @@ struct LegArgs {
   const __half* A; int64_t a_pitch;
   int runs_per_img, in_img_planes, in_run_planes;
   int kh, kw, c8in;
-  const __half* Bp;           // [cout/64][kh*kw*3][c8in][64][8]
+  const __half* Bp;           // [cout/64][kh*kw*3][c8in][64][8]   (k_leg_batched_tc: stacked layout, see TcState::wstk)
+  int c8u;                    // k_leg_batched_tc: C_in/8 chunks per streamed weight unit
   const float* bias; int n_valid;
   int64_t M;                  // output pixels per run
   __half* out_planes; int64_t out_pitch; int out_run_planes;   // EPI 4
@@ -1329,15 +1334,17 @@ k_leg_batched_tc(LegArgs g, int n_mma, int* __restrict__ err) {
   using Smem = LBSmemT<STAGES, A_MAX>;
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   constexpr int WIN = TILES * 128 + 16;             // pixels per window plane (kw <= 15)
-  constexpr uint32_t TMEM_COLS = TILES * 64;
+  constexpr uint32_t TMEM_COLS = TILES * 128;      // per tile: columns [0, n_mma) and [n_mma, 2 n_mma), summed by the epilogue
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t row0 = (int64_t)blockIdx.x * (TILES * 128);
   const int y = blockIdx.y, nh = blockIdx.z;
   const int64_t in_base = (int64_t)(y / g.runs_per_img) * g.in_img_planes + (int64_t)(y % g.runs_per_img) * g.in_run_planes;
   const int n_planes = g.kh * 2 * g.c8in;
-  const int n_slabs = g.kh * g.kw * 3;
-  const uint32_t b_bytes = (uint32_t)g.c8in * 64 * 16;
-  const int grp = (int)(LR_B_MAX / b_bytes) > 0 ? (int)(LR_B_MAX / b_bytes) : 1;      // slabs per ring stage
+  const int R = 2 * n_mma;                          // stacked weight rows per unit: [hi | lo]
+  const int kc_n = g.c8in / g.c8u;
+  const int n_slabs = g.kh * g.kw * kc_n;           // streamed weight units: (dh, dw, C_in chunk)
+  const uint32_t b_bytes = (uint32_t)g.c8u * R * 16;
+  const int grp = (int)(LR_B_MAX / b_bytes) > 0 ? (int)(LR_B_MAX / b_bytes) : 1;      // units per ring stage
   int nt = (int)((g.M - row0 + 127) / 128);         // tiles of this CTA that hold valid pixels
   if (nt > TILES) nt = TILES;
 
@@ -1371,15 +1378,16 @@ k_leg_batched_tc(LegArgs g, int n_mma, int* __restrict__ err) {
       if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_f16(128, n_mma);
+    const uint32_t idesc2 = make_idesc_f16(128, R), idesc1 = make_idesc_f16(128, n_mma);
     const bool leader = elect_one() != 0;
     const uint64_t ad0 = make_desc_kmajor_noswizzle(smem_u32(S.A), WIN * 16, 128);
-    const uint64_t bd0 = make_desc_kmajor_noswizzle(smem_u32(S.B[0]), 64 * 16, 128);
+    const uint64_t bd0 = make_desc_kmajor_noswizzle(smem_u32(S.B[0]), R * 16, 128);
     const uint32_t ad_hi = (uint32_t)(ad0 >> 32), ad_lo = (uint32_t)ad0;
     const uint32_t bd_hi = (uint32_t)(bd0 >> 32), bd_lo = (uint32_t)bd0;
+    const uint32_t lo_off = (uint32_t)((g.c8in * (WIN * 16)) >> 4);    // hi planes -> lo planes of the same input row
     TC_WAIT(&S.a_full, 0, 812);
     uint32_t sg = 0, ph = 0, first = 1;
-    int term = 0, dw = 0, dh = 0;                   // slab = (dh, dw, term); x*w ~= xh*wh + xl*wh + xh*wl
+    int kc = 0, dw = 0, dh = 0;                     // unit = (dh, dw, kc)
 #pragma unroll 1
     for (int sl = 0; sl < n_slabs; sl += grp) {
       const int cnt = (n_slabs - sl < grp) ? n_slabs - sl : grp;
@@ -1387,24 +1395,25 @@ k_leg_batched_tc(LegArgs g, int n_mma, int* __restrict__ err) {
       fence_after_sync();
       for (int j = 0; j < cnt; ++j) {
         if (leader) {
-          const uint32_t kind = (term == 1) ? 1u : 0u;
-          const uint32_t a_k = ad_lo + ((((dh * 2 + kind) * g.c8in) * (WIN * 16) + dw * 16) >> 4);
+          const uint32_t a_k = ad_lo + ((((dh * 2) * g.c8in + kc * g.c8u) * (WIN * 16) + dw * 16) >> 4);
           const uint32_t b_k = bd_lo + ((sg * LR_B_MAX + j * b_bytes) >> 4);
-          for (int c16 = 0; c16 < g.c8in / 2; ++c16) {
-            const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_k + ((c16 * 2 * (64 * 16)) >> 4));
+          for (int c16 = 0; c16 < g.c8u / 2; ++c16) {
+            const uint64_t bd = ((uint64_t)bd_hi << 32) | (uint64_t)(b_k + ((c16 * 2 * (R * 16)) >> 4));
             const uint32_t a_c = a_k + ((c16 * 2 * (WIN * 16)) >> 4);
 #pragma unroll
             for (int t = 0; t < TILES; ++t) {
               if (t < nt) {
-                const uint64_t ad = ((uint64_t)ad_hi << 32) | (uint64_t)(a_c + ((t * 128 * 16) >> 4));
-                mma_ss(tmem + t * 64, ad, bd, idesc, first ? 0u : 1u);
+                const uint64_t adh = ((uint64_t)ad_hi << 32) | (uint64_t)(a_c + ((t * 128 * 16) >> 4));
+                const uint64_t adl = ((uint64_t)ad_hi << 32) | (uint64_t)(a_c + lo_off + ((t * 128 * 16) >> 4));
+                mma_ss(tmem + t * 128, adh, bd, idesc2, first ? 0u : 1u);     // xh * [wh | wl] -> columns [0, 2 n_mma)
+                mma_ss(tmem + t * 128, adl, bd, idesc1, 1u);                  // xl * wh        -> columns [0, n_mma)
               }
             }
             first = 0;
           }
         }
         first = 0;
-        if (++term == 3) { term = 0; if (++dw == g.kw) { dw = 0; ++dh; } }
+        if (++kc == kc_n) { kc = 0; if (++dw == g.kw) { dw = 0; ++dh; } }
       }
       if (leader) commit(&S.empty[sg]);
       __syncwarp();
@@ -1422,13 +1431,14 @@ k_leg_batched_tc(LegArgs g, int n_mma, int* __restrict__ err) {
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 16) {
         if (nh * 64 + c0 >= g.n_valid) break;         // warp-uniform
-        uint32_t u[16];
-        tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * 64 + c0, u);
+        uint32_t u[16], u2[16];
+        tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * 128 + c0, u);
+        tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * 128 + n_mma + c0, u2);
         tmem_ld_wait();
         if (r < g.M) {
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(u[j]);
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(u[j]) + __uint_as_float(u2[j]);
           if (EPI == 4) {
 #pragma unroll
             for (int h8 = 0; h8 < 2; ++h8) {
@@ -2043,6 +2053,7 @@ void tc_free(ovn_handle* h) {
   for (void* b : bufs) if (b) cudaFree(b);
   for (int l = 0; l < kMaxLegLayers; ++l) {
     if (t->wres[l]) cudaFree(t->wres[l]);
+    if (t->wstk[l]) cudaFree(t->wstk[l]);
   }
   if (t->pb_l16) cudaFree(t->pb_l16);
   if (t->pb_lc) cudaFree(t->pb_lc);
@@ -2167,6 +2178,31 @@ int tc_pack_weights(ovn_handle* h) {
             }
       if ((rc2 = upload_vec(h, &t->wres[l], br)) != OVN_OK) return rc2;
     }
+    {
+      // batched kernel: hi | lo stacked along N (TcState::wstk)
+      const int n_mma = L.cout >= 64 ? 64 : ((L.cout + 15) / 16) * 16, R = 2 * n_mma;
+      int c8u = c8in;
+      while (c8u > 2 && (size_t)c8u * R * 16 > (size_t)LR_B_MAX) c8u /= 2;
+      if (c8in % c8u != 0 || c8u % 2 != 0 || (size_t)c8u * R * 16 > (size_t)LR_B_MAX)
+        OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "tensor-core leg: layer %s weight unit does not fit the ring", L.name);
+      const int kc_n = c8in / c8u, taps = L.kh * L.kw;
+      std::vector<__half> bs((size_t)nz * taps * c8in * R * 8, __float2half(0.f));
+      for (int z = 0; z < nz; ++z)
+        for (int tap = 0; tap < taps; ++tap)
+          for (int c8 = 0; c8 < c8in; ++c8)
+            for (int n = 0; n < n_mma && z * 64 + n < L.cout; ++n)
+              for (int k = 0; k < 8; ++k) {
+                const float wf = w.kernel[((size_t)tap * L.cin + c8 * 8 + k) * L.cout + z * 64 + n];
+                const __half wh = __float2half(wf);
+                const __half wl = __float2half(wf - __half2float(wh));
+                const size_t unit = ((size_t)z * taps + tap) * kc_n + c8 / c8u;
+                const size_t base = (unit * c8u + c8 % c8u) * R;
+                bs[(base + n) * 8 + k] = wh;
+                bs[(base + n_mma + n) * 8 + k] = wl;
+              }
+      if ((rc2 = upload_vec(h, &t->wstk[l], bs)) != OVN_OK) return rc2;
+      t->stk_c8u[l] = c8u;
+    }
   }
   {
     // ---- layer 1 on tensor cores: W'[dh][j][parity*C + c][n] = W[dh][2j + parity][c][n]  (kw' = ceil(kw / 2))
@@ -2175,31 +2211,37 @@ int tc_pack_weights(ovn_handle* h) {
     const int kwp = (L.kw + 1) / 2;
     // measured (batch 64, us/scan, whole leg): C = 25: 52.4 direct -> 41.8 here; C = 4: 16.4 direct -> 20.9 here
     // (N = 16 MMAs are bound by the shared-memory read of A), so only wide inputs take this path
-    t->l1_tc = L.cin > 8 && L.sw == 2 && L.cout == 16 && kwp <= 16 &&
-               (size_t)L.kh * 2 * c8in * (128 + 16) * 16 <= (size_t)LB_A_FAT && (size_t)c8in * 64 * 16 <= (size_t)LR_B_MAX;
+    const char* l1_env = getenv("OVN_L1_TC");                    // measurement switch: 1 = always, 0 = never
+    const bool l1_wide = l1_env ? (l1_env[0] == '1') : (L.cin > 8);
+    t->l1_tc = l1_wide && L.sw == 2 && L.cout == 16 && kwp <= 16 &&
+               (size_t)L.kh * 2 * c8in * (128 + 16) * 16 <= (size_t)LB_A_FAT && c8in % 2 == 0 && (c8in & (c8in - 1)) == 0;
     if (t->l1_tc) {
       const LayerWeights& w = h->host_w[L.name];
-      const int nsl = L.kh * kwp * 3;
-      std::vector<__half> br((size_t)nsl * c8in * 64 * 8, __float2half(0.f));
+      const int n_mma = 16, R = 2 * n_mma, taps = L.kh * kwp;
+      int c8u = c8in;
+      while (c8u > 2 && (size_t)c8u * R * 16 > (size_t)LR_B_MAX) c8u /= 2;
+      const int kc_n = c8in / c8u;
+      std::vector<__half> bs((size_t)taps * c8in * R * 8, __float2half(0.f));
       for (int dh = 0; dh < L.kh; ++dh)
         for (int j = 0; j < kwp; ++j)
-          for (int term = 0; term < 3; ++term) {
-            const int sl = (dh * kwp + j) * 3 + term;
-            for (int c8 = 0; c8 < c8in; ++c8)
-              for (int n = 0; n < L.cout; ++n)
-                for (int k = 0; k < 8; ++k) {
-                  const int ch = c8 * 8 + k;
-                  if (ch >= 2 * L.cin) continue;
-                  const int parity = ch / L.cin, c = ch - parity * L.cin, dw = 2 * j + parity;
-                  if (dw >= L.kw) continue;
-                  const float wf = w.kernel[(((size_t)dh * L.kw + dw) * L.cin + c) * L.cout + n];
-                  const __half wh = __float2half(wf);
-                  const __half wl = __float2half(wf - __half2float(wh));
-                  br[(((size_t)sl * c8in + c8) * 64 + n) * 8 + k] = (term == 2) ? wl : wh;
-                }
-          }
+          for (int c8 = 0; c8 < c8in; ++c8)
+            for (int n = 0; n < L.cout; ++n)
+              for (int k = 0; k < 8; ++k) {
+                const int ch = c8 * 8 + k;
+                if (ch >= 2 * L.cin) continue;
+                const int parity = ch / L.cin, c = ch - parity * L.cin, dw = 2 * j + parity;
+                if (dw >= L.kw) continue;
+                const float wf = w.kernel[(((size_t)dh * L.kw + dw) * L.cin + c) * L.cout + n];
+                const __half wh = __float2half(wf);
+                const __half wl = __float2half(wf - __half2float(wh));
+                const size_t unit = (size_t)(dh * kwp + j) * kc_n + c8 / c8u;
+                const size_t base = (unit * c8u + c8 % c8u) * R;
+                bs[(base + n) * 8 + k] = wh;
+                bs[(base + n_mma + n) * 8 + k] = wl;
+              }
       int rc2;
-      if ((rc2 = upload_vec(h, &t->wres[0], br)) != OVN_OK) return rc2;
+      if ((rc2 = upload_vec(h, &t->wstk[0], bs)) != OVN_OK) return rc2;
+      t->stk_c8u[0] = c8u;
       t->l1_c8in = c8in;
       const size_t bytes = (size_t)h->cfg.max_batch_scans * L.h_in * 2 * c8in * ((L.w_in + 1) / 2) * 16 + 32768;
       OVN_CUDA(h, cudaMalloc(&t->in_planes, bytes));
@@ -2290,7 +2332,8 @@ int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cuda
       OVN_LAUNCH_CHECK(h);
       LegArgs la = {};
       la.A = t->in_planes; la.a_pitch = Wh; la.runs_per_img = L.h_out; la.in_img_planes = L.h_in * 2 * c8in;
-      la.in_run_planes = L.sh * 2 * c8in; la.kh = L.kh; la.kw = kwp; la.c8in = c8in; la.Bp = t->wres[0];
+      la.in_run_planes = L.sh * 2 * c8in; la.kh = L.kh; la.kw = kwp; la.c8in = c8in; la.Bp = t->wstk[0];
+      la.c8u = t->stk_c8u[0];
       la.bias = h->d_b[0]; la.n_valid = L.cout; la.M = L.w_out; la.out_planes = t->actp[0]; la.out_pitch = L.w_out;
       la.out_run_planes = 2 * (L.cout / 8); la.out_f32 = nullptr; la.n_split = 1;
       const size_t win2 = (size_t)L.kh * 2 * c8in * (2 * 128 + 16) * 16, win1 = (size_t)L.kh * 2 * c8in * (128 + 16) * 16;
@@ -2378,6 +2421,7 @@ int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cuda
         OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "tensor-core leg: layer %s window does not fit shared memory", L.name);
       const dim3 grid((unsigned)((L.w_out + T * 128 - 1) / (T * 128)), (unsigned)(n * L.h_out), (unsigned)nz);
       int n_mma = L.cout >= 64 ? 64 : ((L.cout + 15) / 16) * 16;          // MMA N (multiple of 16 for M = 128)
+      la.Bp = t->wstk[l]; la.c8u = t->stk_c8u[l];
 #define OVN_LEG_BATCHED(E, TT) k_leg_batched_tc<E, TT><<<grid, G_THREADS, sizeof(LBSmem), s>>>(la, n_mma, h->d_err)
       if (last) { if (T == 4) OVN_LEG_BATCHED(3, 4); else if (T == 2) OVN_LEG_BATCHED(3, 2); else OVN_LEG_BATCHED(3, 1); }
       else { if (T == 4) OVN_LEG_BATCHED(4, 4); else if (T == 2) OVN_LEG_BATCHED(4, 2); else OVN_LEG_BATCHED(4, 1); }
