@@ -506,7 +506,7 @@ def measure_extras(args, eng, w, dev, rank, world, local, timed, q_dev, q_host, 
   if rank == 0:
     try:
       use = {'use_intensity': True, 'use_class_probabilities': True}
-      eng25 = Engine(use=use, model=MODEL, precision=args.precision, device=local, max_batch_scans=64, max_batch_pairs=1)
+      eng25 = Engine(use=use, model=MODEL, precision=args.precision, device=local, max_batch_scans=256, max_batch_pairs=1)
       eng25.load_weights(make_weights(25))
       x_small = torch.from_numpy(synth.range_like_images(5, 8, 25)).to(dev)
       x25 = x_small.repeat(32, 1, 1, 1)                      # 256 scans, 1.47 GB of NHWC input (> L2)

@@ -54,6 +54,11 @@ struct TcState {
   // with rows [0, n_mma) = hi, [n_mma, 2 n_mma) = lo: x*w ~= xh*[wh; wl] (one MMA, N = 2 n_mma) + xl*wh (N = n_mma)
   __half* wstk[kMaxLegLayers] = {};
   int stk_c8u[kMaxLegLayers] = {};
+  // layers with 128 output channels: all of them in one CTA (n_mma = 128, 256 stacked rows), so that the
+  // activation window is read once instead of once per 64-channel half
+  __half* wstkw[kMaxLegLayers] = {};
+  int stkw_c8u[kMaxLegLayers] = {};
+  bool leg_wide = true;
   __half* actp[2] = {nullptr, nullptr};
   // layer 1 on tensor cores (batched encode): the stride-2 columns are de-interleaved into even / odd planes, which
   // turns the 5 x 15 stride-(2,2) conv over C channels into a 5 x 8 stride-(2,1) conv over 2C channels
@@ -1320,7 +1325,7 @@ template <int STAGES, int A_MAX>
 struct LBSmemT {
   uint8_t A[A_MAX];
   uint8_t B[STAGES][LR_B_MAX];
-  float bias[64];
+  float bias[128];
   uint64_t a_full, full[STAGES], empty[STAGES], d_full;
   uint32_t tmem_base;
 };
@@ -1334,7 +1339,10 @@ k_leg_batched_tc(LegArgs g, int n_mma, int* __restrict__ err) {
   using Smem = LBSmemT<STAGES, A_MAX>;
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   constexpr int WIN = TILES * 128 + 16;             // pixels per window plane (kw <= 15)
-  constexpr uint32_t TMEM_COLS = TILES * 128;      // per tile: columns [0, n_mma) and [n_mma, 2 n_mma), summed by the epilogue
+  // per tile: accumulator columns [0, n_mma) and [n_mma, 2 n_mma), summed by the epilogue (n_mma = 128: TILES <= 2)
+  const uint32_t tcol = n_mma > 64 ? 256u : 128u;
+  const uint32_t TMEM_COLS = TILES * tcol;
+  const int n_cols = n_mma > 64 ? 128 : 64;         // output channels of this CTA
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t row0 = (int64_t)blockIdx.x * (TILES * 128);
   const int y = blockIdx.y, nh = blockIdx.z;
@@ -1354,7 +1362,7 @@ k_leg_batched_tc(LegArgs g, int n_mma, int* __restrict__ err) {
     mbar_init(&S.d_full, 1);
     mbar_fence_init();
   }
-  if (tid < 64) S.bias[tid] = (nh * 64 + tid < g.n_valid) ? g.bias[nh * 64 + tid] : 0.f;
+  if (tid < 128) S.bias[tid] = (nh * 64 + tid < g.n_valid) ? g.bias[nh * 64 + tid] : 0.f;
   if (warp == 2) tmem_alloc(&S.tmem_base, TMEM_COLS);
   fence_before_sync();
   __syncthreads();
@@ -1405,8 +1413,8 @@ k_leg_batched_tc(LegArgs g, int n_mma, int* __restrict__ err) {
               if (t < nt) {
                 const uint64_t adh = ((uint64_t)ad_hi << 32) | (uint64_t)(a_c + ((t * 128 * 16) >> 4));
                 const uint64_t adl = ((uint64_t)ad_hi << 32) | (uint64_t)(a_c + lo_off + ((t * 128 * 16) >> 4));
-                mma_ss(tmem + t * 128, adh, bd, idesc2, first ? 0u : 1u);     // xh * [wh | wl] -> columns [0, 2 n_mma)
-                mma_ss(tmem + t * 128, adl, bd, idesc1, 1u);                  // xl * wh        -> columns [0, n_mma)
+                mma_ss(tmem + t * tcol, adh, bd, idesc2, first ? 0u : 1u);     // xh * [wh | wl] -> columns [0, 2 n_mma)
+                mma_ss(tmem + t * tcol, adl, bd, idesc1, 1u);                  // xl * wh        -> columns [0, n_mma)
               }
             }
             first = 0;
@@ -1429,11 +1437,11 @@ k_leg_batched_tc(LegArgs g, int n_mma, int* __restrict__ err) {
     for (int t = 0; t < nt; ++t) {
       const int64_t r = row0 + t * 128 + q * 32 + lane;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 16) {
+      for (int c0 = 0; c0 < n_cols; c0 += 16) {
         if (nh * 64 + c0 >= g.n_valid) break;         // warp-uniform
         uint32_t u[16], u2[16];
-        tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * 128 + c0, u);
-        tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * 128 + n_mma + c0, u2);
+        tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * tcol + c0, u);
+        tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + t * tcol + n_mma + c0, u2);
         tmem_ld_wait();
         if (r < g.M) {
           float v[16];
@@ -2054,6 +2062,7 @@ void tc_free(ovn_handle* h) {
   for (int l = 0; l < kMaxLegLayers; ++l) {
     if (t->wres[l]) cudaFree(t->wres[l]);
     if (t->wstk[l]) cudaFree(t->wstk[l]);
+    if (t->wstkw[l]) cudaFree(t->wstkw[l]);
   }
   if (t->pb_l16) cudaFree(t->pb_l16);
   if (t->pb_lc) cudaFree(t->pb_lc);
@@ -2203,6 +2212,33 @@ int tc_pack_weights(ovn_handle* h) {
       if ((rc2 = upload_vec(h, &t->wstk[l], bs)) != OVN_OK) return rc2;
       t->stk_c8u[l] = c8u;
     }
+    if (L.cout == 128) {
+      const int n_mma = 128, R = 256, taps = L.kh * L.kw;
+      int c8u = c8in;
+      while (c8u > 2 && (size_t)c8u * R * 16 > (size_t)LR_B_MAX) c8u /= 2;
+      if (c8in % c8u == 0 && c8u % 2 == 0 && (size_t)c8u * R * 16 <= (size_t)LR_B_MAX) {
+        const int kc_n = c8in / c8u;
+        std::vector<__half> bs((size_t)taps * c8in * R * 8, __float2half(0.f));
+        for (int tap = 0; tap < taps; ++tap)
+          for (int c8 = 0; c8 < c8in; ++c8)
+            for (int n = 0; n < n_mma; ++n)
+              for (int k = 0; k < 8; ++k) {
+                const float wf = w.kernel[((size_t)tap * L.cin + c8 * 8 + k) * L.cout + n];
+                const __half wh = __float2half(wf);
+                const __half wl = __float2half(wf - __half2float(wh));
+                const size_t unit = (size_t)tap * kc_n + c8 / c8u;
+                const size_t base = (unit * c8u + c8 % c8u) * R;
+                bs[(base + n) * 8 + k] = wh;
+                bs[(base + n_mma + n) * 8 + k] = wl;
+              }
+        if ((rc2 = upload_vec(h, &t->wstkw[l], bs)) != OVN_OK) return rc2;
+        t->stkw_c8u[l] = c8u;
+      }
+    }
+  }
+  {
+    const char* e = getenv("OVN_LEG_WIDE");                      // measurement switch: 0 = 64-channel halves in two CTAs
+    t->leg_wide = !(e && e[0] == '0');
   }
   {
     // ---- layer 1 on tensor cores: W'[dh][j][parity*C + c][n] = W[dh][2j + parity][c][n]  (kw' = ceil(kw / 2))
@@ -2410,18 +2446,33 @@ int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cuda
       if (last) OVN_CUDA(h, cudaLaunchKernelEx(&lc, k_leg_resident_tc<3>, la, h->d_err));
       else OVN_CUDA(h, cudaLaunchKernelEx(&lc, k_leg_resident_tc<4>, la, h->d_err));
     } else {
-      // largest tile count whose activation window fits and that still gives every SM a CTA
+      const bool wide = t->leg_wide && L.cout == 128 && t->wstkw[l] != nullptr;
+      const int nzb = wide ? 1 : nz;
       int T = 1;
-      for (int cand = 4; cand >= 2; cand >>= 1) {
-        const size_t win_bytes = (size_t)L.kh * 2 * (L.cin / 8) * (cand * 128 + 16) * 16;
-        const int ctas = ((L.w_out + cand * 128 - 1) / (cand * 128)) * n * L.h_out * nz;
-        if (win_bytes <= (size_t)LB_A_MAX && ctas >= h->sm_count) { T = cand; break; }
+      if (wide) {
+        // 256 accumulator columns per tile: at most two tiles; fewest (waves x tiles), ties to the larger tile count
+        long best = -1;
+        for (int cand = 2; cand >= 1; --cand) {
+          const size_t win_bytes = (size_t)L.kh * 2 * (L.cin / 8) * (cand * 128 + 16) * 16;
+          if (win_bytes > (size_t)LB_A_MAX) continue;
+          const int ctas = ((L.w_out + cand * 128 - 1) / (cand * 128)) * n * L.h_out;
+          const long cost = (long)((ctas + h->sm_count - 1) / h->sm_count) * cand;
+          if (best < 0 || cost < best) { best = cost; T = cand; }
+        }
+      } else {
+        // largest tile count whose activation window fits and that still gives every SM a CTA
+        for (int cand = 4; cand >= 2; cand >>= 1) {
+          const size_t win_bytes = (size_t)L.kh * 2 * (L.cin / 8) * (cand * 128 + 16) * 16;
+          const int ctas = ((L.w_out + cand * 128 - 1) / (cand * 128)) * n * L.h_out * nz;
+          if (win_bytes <= (size_t)LB_A_MAX && ctas >= h->sm_count) { T = cand; break; }
+        }
       }
       if ((size_t)L.kh * 2 * (L.cin / 8) * (128 + 16) * 16 > (size_t)LB_A_MAX)
         OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "tensor-core leg: layer %s window does not fit shared memory", L.name);
-      const dim3 grid((unsigned)((L.w_out + T * 128 - 1) / (T * 128)), (unsigned)(n * L.h_out), (unsigned)nz);
-      int n_mma = L.cout >= 64 ? 64 : ((L.cout + 15) / 16) * 16;          // MMA N (multiple of 16 for M = 128)
-      la.Bp = t->wstk[l]; la.c8u = t->stk_c8u[l];
+      const dim3 grid((unsigned)((L.w_out + T * 128 - 1) / (T * 128)), (unsigned)(n * L.h_out), (unsigned)nzb);
+      int n_mma = wide ? 128 : (L.cout >= 64 ? 64 : ((L.cout + 15) / 16) * 16);   // MMA N (multiple of 16 for M = 128)
+      la.Bp = wide ? t->wstkw[l] : t->wstk[l];
+      la.c8u = wide ? t->stkw_c8u[l] : t->stk_c8u[l];
 #define OVN_LEG_BATCHED(E, TT) k_leg_batched_tc<E, TT><<<grid, G_THREADS, sizeof(LBSmem), s>>>(la, n_mma, h->d_err)
       if (last) { if (T == 4) OVN_LEG_BATCHED(3, 4); else if (T == 2) OVN_LEG_BATCHED(3, 2); else OVN_LEG_BATCHED(3, 1); }
       else { if (T == 4) OVN_LEG_BATCHED(4, 4); else if (T == 2) OVN_LEG_BATCHED(4, 2); else OVN_LEG_BATCHED(4, 1); }

@@ -9,7 +9,9 @@ from overlapnet_b200.engine import Engine
 sys.path.insert(0, ROOT)
 import bench
 
-def run(channels, use, batch, total, l1_tc=None):
+def run(channels, use, batch, total, l1_tc=None, wide=None):
+  if wide is None: os.environ.pop('OVN_LEG_WIDE', None)
+  else: os.environ['OVN_LEG_WIDE'] = wide
   if l1_tc is None: os.environ.pop('OVN_L1_TC', None)
   else: os.environ['OVN_L1_TC'] = l1_tc
   eng = Engine(use=use, model=bench.MODEL, precision='f16_tc', max_batch_scans=batch, max_batch_pairs=1)
@@ -23,14 +25,16 @@ def run(channels, use, batch, total, l1_tc=None):
   b.record(); torch.cuda.synchronize()
   ms = a.elapsed_time(b) / 5
   flop = {4: bench.FLOP_LEG_C4, 25: bench.FLOP_LEG_C25}.get(channels, bench.FLOP_LEG_C4)
-  print('C=%d batch=%d total=%d l1_tc=%s: %.3f ms  %.2f us/scan  %.1f TFLOP/s algorithmic (x3 issued)' %
-        (channels, batch, total, l1_tc, ms, ms * 1e3 / total, total * flop / 1e12 / (ms * 1e-3)))
+  print('C=%d batch=%d total=%d l1_tc=%s wide=%s: %.3f ms  %.2f us/scan  %.1f TFLOP/s algorithmic (x3 issued)' %
+        (channels, batch, total, l1_tc, wide, ms, ms * 1e3 / total, total * flop / 1e12 / (ms * 1e-3)))
   eng.close()
 
 if __name__ == '__main__':
-  run(4, {}, 64, 256, '0')
-  run(4, {}, 64, 256, '1')
+  sem = {'use_intensity': True, 'use_class_probabilities': True}
+  run(4, {}, 64, 256, wide='0')
+  run(4, {}, 64, 256)
+  run(4, {}, 256, 256, wide='0')
   run(4, {}, 256, 256)
-  run(25, {'use_intensity': True, 'use_class_probabilities': True}, 64, 256, '0')
-  run(25, {'use_intensity': True, 'use_class_probabilities': True}, 64, 256, '1')
-  run(25, {'use_intensity': True, 'use_class_probabilities': True}, 256, 256)
+  run(25, sem, 64, 256)
+  run(25, sem, 256, 256, wide='0')
+  run(25, sem, 256, 256)
