@@ -62,8 +62,11 @@ struct TcState {
   __half* actp[2] = {nullptr, nullptr};
   // layer 1 on tensor cores (batched encode): the stride-2 columns are de-interleaved into even / odd planes, which
   // turns the 5 x 15 stride-(2,2) conv over C channels into a 5 x 8 stride-(2,1) conv over 2C channels
-  __half* in_planes = nullptr;          // [max_batch_scans][H][hi,lo][l1_c8in][ceil(W/2)][8]
-  int l1_c8in = 0;                      // (2C rounded up to a multiple of 16) / 8
+  // Narrow inputs (C <= 8) additionally fold the kh kernel rows into K (channel' = (dh * 2 + parity) * C + c, one
+  // plane set per OUTPUT row): K = 16 per MMA would otherwise be half padding.
+  __half* in_planes = nullptr;          // [max_batch_scans][rows][hi,lo][l1_c8in][ceil(W/2)][8]; rows = H (l1_fold = 1) or H_out
+  int l1_c8in = 0;                      // (l1_fold * 2C rounded up to a multiple of 16) / 8
+  int l1_fold = 1;                      // kernel rows folded into the channel dimension (1 or kh)
   bool l1_tc = false;
   float* leg_part = nullptr;     // split-K partial tiles of the latency-mode leg: [kLegPartTiles][128 x 64] fp32
   int* leg_counters = nullptr;   // [kLegPartTiles * 4] arrival counters (always left at zero)
@@ -2018,29 +2021,34 @@ k_leg_layer1_small(const float* __restrict__ x, const float* __restrict__ w, con
   *reinterpret_cast<uint4*>(out + ((size_t)(plane_hi + C8) * W_out + xo) * 8) = *reinterpret_cast<const uint4*>(lo);
 }
 
-// fp32 NHWC [n][H][W][C] -> hi/lo fp16 planes [n][H][hi,lo][c8in][ceil(W/2)][8] with channel' = parity * C + c
-// (parity = column & 1): the input of the tensor-core layer 1 (see TcState::in_planes)
+// fp32 NHWC [n][H][W][C] -> hi/lo fp16 planes [n][rows][hi,lo][c8in][ceil(W/2)][8], the input of the tensor-core
+// layer 1 (see TcState::in_planes).  channel' = (f * 2 + parity) * C + c with parity = column & 1 and f the folded
+// kernel row: fold = 1: rows = H, plane row r is input row r; fold = kh: rows = H_out, plane row r holds input
+// rows r * sh + f.
 __global__ void __launch_bounds__(256)
-k_input_to_parity_planes(const float* __restrict__ x, int64_t total, int H, int W, int C, int c8in, int Wh,
-                         __half* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // (img*H + h, c8, w')
+k_input_to_parity_planes(const float* __restrict__ x, int64_t total, int H, int W, int C, int c8in, int Wh, int rows,
+                         int fold, int sh, __half* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // (img * rows + r, c8, w')
   if (i >= total) return;
   const int wp = (int)(i % Wh);
-  int64_t r = i / Wh;
-  const int c8 = (int)(r % c8in); r /= c8in;                               // r = img*H + h
+  const int rc = (int)(i / Wh);                                            // (img * rows + row) * c8in + c8 fits 32 bits
+  const int c8 = rc % c8in, r = rc / c8in;
+  const int img = r / rows, row = r - img * rows;
   __half hi[8], lo[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int ch = c8 * 8 + e;
     float v = 0.f;
-    if (ch < 2 * C) {
-      const int parity = ch / C, c = ch - parity * C, w = 2 * wp + parity;
-      if (w < W) v = __ldg(x + (r * W + w) * (int64_t)C + c);
+    if (ch < fold * 2 * C) {
+      const int f = ch / (2 * C), rem = ch - f * 2 * C;
+      const int parity = rem / C, c = rem - parity * C, w = 2 * wp + parity;
+      const int in_row = (fold == 1) ? row : row * sh + f;
+      if (w < W && in_row < H) v = __ldg(x + (((int64_t)img * H + in_row) * W + w) * C + c);
     }
     hi[e] = __float2half_rn(v);
     lo[e] = __float2half_rn(v - __half2float(hi[e]));
   }
-  const int64_t plane_hi = r * (2 * c8in) + c8;
+  const int64_t plane_hi = (int64_t)r * (2 * c8in) + c8;
   *reinterpret_cast<uint4*>(out + ((size_t)plane_hi * Wh + wp) * 8) = *reinterpret_cast<const uint4*>(hi);
   *reinterpret_cast<uint4*>(out + ((size_t)(plane_hi + c8in) * Wh + wp) * 8) = *reinterpret_cast<const uint4*>(lo);
 }
@@ -2241,36 +2249,43 @@ int tc_pack_weights(ovn_handle* h) {
     t->leg_wide = !(e && e[0] == '0');
   }
   {
-    // ---- layer 1 on tensor cores: W'[dh][j][parity*C + c][n] = W[dh][2j + parity][c][n]  (kw' = ceil(kw / 2))
+    // ---- layer 1 on tensor cores: W'[dh'][j][(f * 2 + parity) * C + c][n] = W[dh][2j + parity][c][n]  (kw' = ceil(kw / 2);
+    // fold = 1: dh = dh', f = 0;  fold = kh: dh = f, dh' = 0)
     const ConvSpec& L = h->leg[0];
-    const int c8in = (((2 * L.cin + 7) / 8) + 1) & ~1;
+    // measured (batch 64, us/scan, whole leg), OVN_L1_TC = 0 (SIMT) / 1 (column planes) / 2 (column planes + folded rows):
+    // C = 25: 49.1 / 24.4 / -;  C = 4: 12.2 / 13.2 / 11.7;  C = 5: 14.2 / - / 12.6   (profiles/r2_leg_stacked.txt)
+    const char* l1_env = getenv("OVN_L1_TC");
+    const int mode = l1_env ? (l1_env[0] - '0') : (L.cin > 8 ? 1 : 2);
+    const int fold = (mode == 2) ? L.kh : 1;
+    const int khp = L.kh / fold;
+    const int c8in = (((fold * 2 * L.cin + 7) / 8) + 1) & ~1;
     const int kwp = (L.kw + 1) / 2;
-    // measured (batch 64, us/scan, whole leg): C = 25: 52.4 direct -> 41.8 here; C = 4: 16.4 direct -> 20.9 here
-    // (N = 16 MMAs are bound by the shared-memory read of A), so only wide inputs take this path
-    const char* l1_env = getenv("OVN_L1_TC");                    // measurement switch: 1 = always, 0 = never
-    const bool l1_wide = l1_env ? (l1_env[0] == '1') : (L.cin > 8);
-    t->l1_tc = l1_wide && L.sw == 2 && L.cout == 16 && kwp <= 16 &&
-               (size_t)L.kh * 2 * c8in * (128 + 16) * 16 <= (size_t)LB_A_FAT && c8in % 2 == 0 && (c8in & (c8in - 1)) == 0;
+    const int n_mma = 16, R = 2 * n_mma;
+    int c8u = 0;
+    for (int cand = c8in; cand >= 2; cand -= 2)
+      if (c8in % cand == 0 && (size_t)cand * R * 16 <= (size_t)LR_B_MAX) { c8u = cand; break; }
+    t->l1_tc = (mode == 1 || mode == 2) && L.sw == 2 && L.cout == 16 && kwp <= 16 && c8u > 0 &&
+               (size_t)khp * 2 * c8in * (128 + 16) * 16 <= (size_t)LB_A_FAT;
     if (t->l1_tc) {
       const LayerWeights& w = h->host_w[L.name];
-      const int n_mma = 16, R = 2 * n_mma, taps = L.kh * kwp;
-      int c8u = c8in;
-      while (c8u > 2 && (size_t)c8u * R * 16 > (size_t)LR_B_MAX) c8u /= 2;
+      const int taps = khp * kwp;
       const int kc_n = c8in / c8u;
       std::vector<__half> bs((size_t)taps * c8in * R * 8, __float2half(0.f));
-      for (int dh = 0; dh < L.kh; ++dh)
+      for (int dhp = 0; dhp < khp; ++dhp)
         for (int j = 0; j < kwp; ++j)
           for (int c8 = 0; c8 < c8in; ++c8)
             for (int n = 0; n < L.cout; ++n)
               for (int k = 0; k < 8; ++k) {
                 const int ch = c8 * 8 + k;
-                if (ch >= 2 * L.cin) continue;
-                const int parity = ch / L.cin, c = ch - parity * L.cin, dw = 2 * j + parity;
+                if (ch >= fold * 2 * L.cin) continue;
+                const int f = ch / (2 * L.cin), rem = ch - f * 2 * L.cin;
+                const int parity = rem / L.cin, c = rem - parity * L.cin, dw = 2 * j + parity;
+                const int dh = (fold == 1) ? dhp : f;
                 if (dw >= L.kw) continue;
                 const float wf = w.kernel[(((size_t)dh * L.kw + dw) * L.cin + c) * L.cout + n];
                 const __half wh = __float2half(wf);
                 const __half wl = __float2half(wf - __half2float(wh));
-                const size_t unit = (size_t)(dh * kwp + j) * kc_n + c8 / c8u;
+                const size_t unit = (size_t)(dhp * kwp + j) * kc_n + c8 / c8u;
                 const size_t base = (unit * c8u + c8 % c8u) * R;
                 bs[(base + n) * 8 + k] = wh;
                 bs[(base + n_mma + n) * 8 + k] = wl;
@@ -2279,7 +2294,9 @@ int tc_pack_weights(ovn_handle* h) {
       if ((rc2 = upload_vec(h, &t->wstk[0], bs)) != OVN_OK) return rc2;
       t->stk_c8u[0] = c8u;
       t->l1_c8in = c8in;
-      const size_t bytes = (size_t)h->cfg.max_batch_scans * L.h_in * 2 * c8in * ((L.w_in + 1) / 2) * 16 + 32768;
+      t->l1_fold = fold;
+      const int rows = (fold == 1) ? L.h_in : L.h_out;
+      const size_t bytes = (size_t)h->cfg.max_batch_scans * rows * 2 * c8in * ((L.w_in + 1) / 2) * 16 + 32768;
       OVN_CUDA(h, cudaMalloc(&t->in_planes, bytes));
       OVN_CUDA(h, cudaMemset(t->in_planes, 0, bytes));
     }
@@ -2360,29 +2377,29 @@ int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cuda
     const size_t w_bytes = (size_t)L.kw * L.cin * L.cout * sizeof(float);        // one kernel row of taps
     const size_t w_all = w_bytes * L.kh;
     if (n > 2 && t->l1_tc) {
-      // batched encode: layer 1 on tensor cores through even / odd column planes
-      const int c8in = t->l1_c8in, Wh = (L.w_in + 1) / 2, kwp = (L.kw + 1) / 2;
-      const int64_t total = (int64_t)n * L.h_in * c8in * Wh;
+      // batched encode: layer 1 on tensor cores through even / odd column planes (kernel rows folded into K for narrow inputs)
+      const int c8in = t->l1_c8in, Wh = (L.w_in + 1) / 2, kwp = (L.kw + 1) / 2, fold = t->l1_fold;
+      const int rows = (fold == 1) ? L.h_in : L.h_out, khp = L.kh / fold;
+      const int64_t total = (int64_t)n * rows * c8in * Wh;
+      if ((int64_t)n * rows * c8in > 0x7fffffffll) OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "tensor-core leg: batch too large for the plane prepass");
       k_input_to_parity_planes<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_input, total, L.h_in, L.w_in, L.cin, c8in, Wh,
-                                                                           t->in_planes);
+                                                                           rows, fold, L.sh, t->in_planes);
       OVN_LAUNCH_CHECK(h);
       LegArgs la = {};
-      la.A = t->in_planes; la.a_pitch = Wh; la.runs_per_img = L.h_out; la.in_img_planes = L.h_in * 2 * c8in;
-      la.in_run_planes = L.sh * 2 * c8in; la.kh = L.kh; la.kw = kwp; la.c8in = c8in; la.Bp = t->wstk[0];
+      la.A = t->in_planes; la.a_pitch = Wh; la.runs_per_img = L.h_out; la.in_img_planes = rows * 2 * c8in;
+      la.in_run_planes = ((fold == 1) ? L.sh : 1) * 2 * c8in; la.kh = khp; la.kw = kwp; la.c8in = c8in; la.Bp = t->wstk[0];
       la.c8u = t->stk_c8u[0];
       la.bias = h->d_b[0]; la.n_valid = L.cout; la.M = L.w_out; la.out_planes = t->actp[0]; la.out_pitch = L.w_out;
       la.out_run_planes = 2 * (L.cout / 8); la.out_f32 = nullptr; la.n_split = 1;
-      const size_t win2 = (size_t)L.kh * 2 * c8in * (2 * 128 + 16) * 16, win1 = (size_t)L.kh * 2 * c8in * (128 + 16) * 16;
-      if (win2 <= (size_t)LB_A_MAX) {
-        const dim3 grid((unsigned)((L.w_out + 255) / 256), (unsigned)(n * L.h_out), 1);
-        k_leg_batched_tc<4, 2><<<grid, G_THREADS, sizeof(LBSmem), s>>>(la, 16, h->d_err);
-      } else if (win1 <= (size_t)LB_A_MAX) {
-        const dim3 grid((unsigned)((L.w_out + 127) / 128), (unsigned)(n * L.h_out), 1);
-        k_leg_batched_tc<4, 1><<<grid, G_THREADS, sizeof(LBSmem), s>>>(la, 16, h->d_err);
-      } else {
-        const dim3 grid((unsigned)((L.w_out + 127) / 128), (unsigned)(n * L.h_out), 1);
-        k_leg_batched_tc<4, 1, 2, LB_A_FAT><<<grid, G_THREADS, sizeof(LBSmemFat), s>>>(la, 16, h->d_err);
-      }
+      const size_t per_px = (size_t)khp * 2 * c8in * 16;
+      int T = 0;
+      for (int cand = 4; cand >= 1; cand >>= 1)
+        if (per_px * (cand * 128 + 16) <= (size_t)LB_A_MAX && (cand == 1 || (cand / 2) * 128 < L.w_out)) { T = cand; break; }
+      const dim3 grid((unsigned)((L.w_out + (T ? T : 1) * 128 - 1) / ((T ? T : 1) * 128)), (unsigned)(n * L.h_out), 1);
+      if (T == 4) k_leg_batched_tc<4, 4><<<grid, G_THREADS, sizeof(LBSmem), s>>>(la, 16, h->d_err);
+      else if (T == 2) k_leg_batched_tc<4, 2><<<grid, G_THREADS, sizeof(LBSmem), s>>>(la, 16, h->d_err);
+      else if (T == 1) k_leg_batched_tc<4, 1><<<grid, G_THREADS, sizeof(LBSmem), s>>>(la, 16, h->d_err);
+      else k_leg_batched_tc<4, 1, 2, LB_A_FAT><<<grid, G_THREADS, sizeof(LBSmemFat), s>>>(la, 16, h->d_err);
     } else if (n <= 2 && w_all <= 200 * 1024 && L.cout % 8 == 0) {
       const unsigned grid = (unsigned)((chunks + 255) / 256);
       if (L.cin == 4)

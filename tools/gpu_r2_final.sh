@@ -8,7 +8,7 @@ timeout 600 python -m pytest tests/test_gpu_network.py -m gpu -q -s -k "leg" > g
 rc=$?
 echo "leg pytest exit $rc"; grep "\[parity\]" gpurun_out/r2_pytest_leg.log
 if [ $rc -ne 0 ]; then tail -30 gpurun_out/r2_pytest_leg.log; export OVN_LEG_WIDE=0; echo "FALLBACK OVN_LEG_WIDE=0"; fi
-if [ $rc -eq 0 ]; then timeout 300 python tools/time_leg.py 2>&1 | tee gpurun_out/r2_time_leg.log; fi
+if [ $rc -eq 0 ]; then timeout 300 python tools/time_leg.py 2 2>&1 | tee gpurun_out/r2_time_leg.log; fi
 timeout 1500 python -m pytest tests -m gpu -q -s > gpurun_out/r2_pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/r2_pytest.log
 tail -6 gpurun_out/r2_pytest.log
@@ -21,5 +21,3 @@ d = json.load(open('gpurun_out/r2_bench2.json'))
 print({k: d[k] for k in ('value', 'ms_per_step')}, d['e2e']['value'], d['parity_check'], d['roofline']['share_of_step'], d['roofline']['frac_burst'])
 print({k: v for k, v in d.get('extras', {}).items()} if 'extras' in d else [k for k in d])
 PY
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 1 --no-extras > gpurun_out/r2_ncu_bench.log 2>&1
-echo "ncu exit $?"

@@ -31,10 +31,9 @@ def run(channels, use, batch, total, l1_tc=None, wide=None):
 
 if __name__ == '__main__':
   sem = {'use_intensity': True, 'use_class_probabilities': True}
-  run(4, {}, 64, 256, wide='0')
-  run(4, {}, 64, 256)
-  run(4, {}, 256, 256, wide='0')
+  for mode in (sys.argv[1:] or ['0', '1', '2']):
+    run(4, {}, 64, 256, l1_tc=mode)
   run(4, {}, 256, 256)
+  run(5, {'use_intensity': True}, 64, 256)
   run(25, sem, 64, 256)
-  run(25, sem, 256, 256, wide='0')
   run(25, sem, 256, 256)
