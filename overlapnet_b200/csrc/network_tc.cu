@@ -2028,25 +2028,31 @@ k_leg_layer1_small(const float* __restrict__ x, const float* __restrict__ w, con
 __global__ void __launch_bounds__(256)
 k_input_to_parity_planes(const float* __restrict__ x, int64_t total, int H, int W, int C, int c8in, int Wh, int rows,
                          int fold, int sh, __half* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // (img * rows + r, c8, w')
+  // thread = (img * rows + row, w', c8) with c8 fastest: the threads of one pixel pair read its 2C contiguous floats,
+  // a warp writes whole 32 B sectors of each plane
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int wp = (int)(i % Wh);
-  const int rc = (int)(i / Wh);                                            // (img * rows + row) * c8in + c8 fits 32 bits
-  const int c8 = rc % c8in, r = rc / c8in;
+  const int c8 = (int)(i % c8in);
+  const int64_t pw = i / c8in;
+  const int wp = (int)(pw % Wh);
+  const int r = (int)(pw / Wh);                                            // img * rows + row fits 32 bits
   const int img = r / rows, row = r - img * rows;
+  const int n_ch = fold * 2 * C;
+  int ch = c8 * 8;
+  int f = ch / (2 * C), rem = ch - f * 2 * C;
+  int parity = rem / C, c = rem - parity * C;
   __half hi[8], lo[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int ch = c8 * 8 + e;
+  for (int e = 0; e < 8; ++e, ++ch) {
     float v = 0.f;
-    if (ch < fold * 2 * C) {
-      const int f = ch / (2 * C), rem = ch - f * 2 * C;
-      const int parity = rem / C, c = rem - parity * C, w = 2 * wp + parity;
+    if (ch < n_ch) {
+      const int w = 2 * wp + parity;
       const int in_row = (fold == 1) ? row : row * sh + f;
       if (w < W && in_row < H) v = __ldg(x + (((int64_t)img * H + in_row) * W + w) * C + c);
     }
     hi[e] = __float2half_rn(v);
     lo[e] = __float2half_rn(v - __half2float(hi[e]));
+    if (++c == C) { c = 0; if (++parity == 2) { parity = 0; ++f; } }
   }
   const int64_t plane_hi = (int64_t)r * (2 * c8in) + c8;
   *reinterpret_cast<uint4*>(out + ((size_t)plane_hi * Wh + wp) * 8) = *reinterpret_cast<const uint4*>(hi);
@@ -2381,7 +2387,7 @@ int leg_forward_tc(ovn_handle* h, const float* d_input, int n, float* d_fv, cuda
       const int c8in = t->l1_c8in, Wh = (L.w_in + 1) / 2, kwp = (L.kw + 1) / 2, fold = t->l1_fold;
       const int rows = (fold == 1) ? L.h_in : L.h_out, khp = L.kh / fold;
       const int64_t total = (int64_t)n * rows * c8in * Wh;
-      if ((int64_t)n * rows * c8in > 0x7fffffffll) OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "tensor-core leg: batch too large for the plane prepass");
+      if ((int64_t)n * rows > 0x7fffffffll) OVN_SET_ERR(h, OVN_ERR_BAD_CONFIG, "tensor-core leg: batch too large for the plane prepass");
       k_input_to_parity_planes<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_input, total, L.h_in, L.w_in, L.cin, c8in, Wh,
                                                                            rows, fold, L.sh, t->in_planes);
       OVN_LAUNCH_CHECK(h);
