@@ -2,10 +2,13 @@
 //
 // Replaces: DeltaLayer + c_conv1 (generateNet.py:15-61,96-100)      -> k_delta_conv1_tc
 //           c_conv2 (+ReLU) (generateNet.py:102-105)                -> k_conv2_sw_tc
-//           c_conv3 (+ReLU), Flatten + Dense(1, sigmoid) (:107-114) -> k_conv3_resident_tc + k_dense_finalize
+//           c_conv3 (+ReLU), Flatten + Dense(1, sigmoid) (:107-114) -> k_conv3_pair_tc (CTA pairs; k_conv3_resident_tc = the
+//                                                                      single-CTA A/B twin) + k_dense_finalize
 //           NormalizedCorrelation2D + argmax (:117-143, infer.py)   -> k_corr_tc + k_corr_finalize
-//           leg Conv2D stack (generateNet.py:149-230)               -> k_leg_layer1_direct, k_leg_resident_tc (1-2 scans),
-//                                                                      k_leg_batched_tc (batched)
+//           leg Conv2D stack (generateNet.py:149-230)               -> k_leg_layer1_small + k_leg_resident_tc (1-2 scans);
+//                                                                      batched: k_input_to_parity_planes (layer-1 input
+//                                                                      as even / odd column planes) + k_leg_batched_tc for
+//                                                                      every layer (hi | lo weights stacked along N)
 //
 // k_delta_conv1_tc (the kernel that decides scan-pairs/s; 83 % of the FLOPs of a pair)
 //   GEMM view per pair:  o1[(i, jb), o] = sum_{dj<15, c<128} |L[i,c] - R[15 jb + dj, c]| W1[dj, c, o]
