@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
       objs = list(ex.map(compile_one, srcs))
     subprocess.check_call([nvcc] + NVCC_FLAGS + ['-shared', '-o', LIB] + objs)
   # standalone known-answer / rate probes of the tcgen05 building blocks (tools, not linked into the library)
-  for name in ('umma_probe', 'cta2_probe'):
+  for name in ('umma_probe', 'cta2_probe', 'ss_rate_probe'):
     probe_src, probe_bin = os.path.join(CSRC, name + '.cu'), os.path.join(HERE, name)
     if os.path.exists(probe_src) and (force or _newer(probe_bin, [probe_src] + deps)):
       subprocess.check_call([nvcc] + NVCC_FLAGS + ['-o', probe_bin, probe_src])
